@@ -1,0 +1,202 @@
+/* probit_b200 — C ABI of the B200-native (sm_100a) GP inference hot path of bb515/probit.
+ *
+ * The reference has no FFI of its own: its boundary is the Python class API
+ * (probit/approximators.py:55-63,154-180,204-210,248-263).  These entry points are what a
+ * `jax.ffi` custom call (or ctypes / DLPack shim) for that path binds; INTEGRATION.md shows the
+ * reference-side binding.  Each function cites the reference code it replaces.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *  - matrices are row-major with an explicit leading dimension (elements, must be even and the
+ *    base pointer 16-byte aligned: the TMA tensor maps require it);
+ *  - all work is enqueued on the caller's stream; functions that must read a convergence scalar
+ *    synchronise that stream themselves and say so;
+ *  - the caller owns every buffer, including scratch (`*_workspace_bytes` tells the size);
+ *  - return value: PB_OK or a negative PB_ERR_* code; `pb_last_error()` holds a thread-local
+ *    message.  Numerical failure (non-positive Cholesky pivot) is reported through the device
+ *    `info` word (LAPACK convention: 1-based index of the failing column), never by aborting.
+ *  - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef PROBIT_B200_H
+#define PROBIT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pb_stream_t; /* == cudaStream_t */
+
+enum {
+    PB_OK = 0,
+    PB_ERR_INVALID = -1,  /* bad argument */
+    PB_ERR_CUDA = -2,     /* CUDA runtime/driver error */
+    PB_ERR_UNSUPPORTED = -3,
+    PB_ERR_NUMERIC = -4   /* non-SPD matrix / NaN detected by a driver that reads `info` */
+};
+
+/* ---- prior (kernel) specification ------------------------------------------------------------
+ * Replaces the mlkernels expression returned by the user's `prior(prior_parameters)`
+ * (examples/regression.py:120-123, examples/classification.py:375,389-391):
+ *   k(x,y) = scale * base( phi(x), phi(y) ),  phi(x) = T(x / stretch_in) / stretch_out,
+ *   T = identity, or the periodic feature map u -> [sin(2 pi u / period), cos(2 pi u / period)].
+ *   base EQ : exp(-0.5 r^2);  base EXP (Matern12): exp(-r);  r = ||phi(x) - phi(y)||_2.          */
+enum { PB_BASE_EQ = 0, PB_BASE_EXP = 1 };
+
+typedef struct pb_kernel_spec {
+    int32_t base;       /* PB_BASE_* */
+    int32_t periodic;   /* 0 / 1 */
+    double scale;       /* c in c * k */
+    double stretch_in;  /* stretch applied before the periodic map (1 if none) */
+    double period;      /* period p (ignored unless periodic) */
+    double stretch_out; /* stretch applied to the features handed to the base kernel */
+} pb_kernel_spec;
+
+/* ---- likelihood specification ---------------------------------------------------------------
+ * Replaces the per-datum callables wrapped at probit/approximators.py:92-104:
+ *  PB_LIK_ORDINAL_PROBIT  log_probit_likelihood (probit/utilities.py:56-57,195-229) and its
+ *                         autodiff gradient/Hessian: ll = log(Z + eps),
+ *                         Z = Phi((b[y+1]-f)/sigma) - Phi((b[y]-f)/sigma), Phi = 0.5(1+erf(z/sqrt2)).
+ *  PB_LIK_GAUSSIAN        log_gaussian_likelihood (probit/utilities.py:60-61).
+ *  PB_LIK_ORDINAL_PROBIT_SAFE  the optional series-expansion gradient/Hessian
+ *                         (probit/utilities.py:88-192); ll is still utilities.py:56-57.           */
+enum { PB_LIK_ORDINAL_PROBIT = 0, PB_LIK_GAUSSIAN = 1, PB_LIK_ORDINAL_PROBIT_SAFE = 2 };
+
+typedef struct pb_likelihood_spec {
+    int32_t kind;            /* PB_LIK_* */
+    int32_t J;               /* number of classes; cutpoints has J+1 entries (ordinal only) */
+    double sigma;            /* likelihood_parameters[0] (noise std) */
+    double eps;              /* the +1e-10 inside log() at probit/utilities.py:57 */
+    const double* cutpoints; /* device, J+1 doubles, b[0] = -inf, b[J] = +inf (ordinal only) */
+    int32_t safe_single_precision; /* SAFE mode: 1 -> BOUNDS["single"], 0 -> BOUNDS["double"] (utilities.py:15) */
+    int32_t _pad;
+} pb_likelihood_spec;
+
+int pb_version(void);
+const char* pb_last_error(void);
+
+/* ---- K4: fused per-datum likelihood (value, gradient, Hessian, third derivative) --------------
+ * probit/approximators.py:96-104.  y is int64 class labels (ordinal) or f64 targets (Gaussian).
+ * Any of ll/g/h/d3 may be NULL.  `batch` independent f-vectors of length n share y (the restart
+ * batch of BASELINE config 5); f and outputs are (batch, n) row-major contiguous.               */
+int pb_likelihood(pb_stream_t stream, const pb_likelihood_spec* lik, const double* f, const void* y,
+                  int64_t n, int64_t batch, double* ll, double* g, double* h, double* d3);
+
+/* ---- K1/K2: Gram assembly ---------------------------------------------------------------------
+ * pb_features: Z[n x Df] = phi(X[n x D]); Df = pb_feature_dim(spec, D).
+ * pb_gram_sym: K = k(X,X) (+ diag_scalar I) (+ diag(diag_vec)); both triangles written (mirror
+ *              store); replaces `prior(theta)(X)` at Laplace.py:7,21,24, VB.py:7,22.
+ * pb_gram_cross: K[n1 x n2] = k(X1, X2); replaces `kernel(X_train, X_test)` approximators.py:173.
+ * Z buffers come from pb_features.                                                              */
+int pb_feature_dim(const pb_kernel_spec* spec, int D);
+int pb_features(pb_stream_t stream, const pb_kernel_spec* spec, const double* X, int64_t n, int D,
+                int64_t ldx, double* Z, int64_t ldz);
+int pb_gram_sym(pb_stream_t stream, const pb_kernel_spec* spec, const double* Z, int64_t n, int Df,
+                int64_t ldz, double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
+int pb_gram_cross(pb_stream_t stream, const pb_kernel_spec* spec, const double* Z1, int64_t n1,
+                  const double* Z2, int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk);
+
+/* B = I + s_i (K_ij + jitter*delta_ij) s_j on the lower triangle (upper left untouched):
+ * the SPD Newton matrix equivalent to `K + diag(1/precision)` (Laplace.py:24, approximators.py:175). */
+int pb_scale_sym_plus_identity(pb_stream_t stream, const double* K, int64_t n, int64_t ldk,
+                               const double* s, double jitter, double* B, int64_t ldb);
+/* A = K + diag_scalar*I on the lower triangle (VB.py:10,25: sigma^2 I + K). */
+int pb_copy_lower_add_diag(pb_stream_t stream, const double* K, int64_t n, int64_t ldk,
+                           double diag_scalar, double* A, int64_t lda);
+
+/* ---- K7: Cholesky ----------------------------------------------------------------------------
+ * In-place lower Cholesky A = L L^T of the row-major lower triangle (strict upper never read or
+ * written).  Replaces B.cholesky at Laplace.py:24, VB.py:10,25 and the LU at solvers.py:24.
+ * Blocked right-looking; trailing updates are FP64 tensor-core (DMMA) tiles fed by TMA.
+ * `info` (device int32): 0, or 1-based column of the first non-positive pivot.                   */
+int64_t pb_potrf_workspace_bytes(int64_t n);
+int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,
+             int64_t workspace_bytes, int32_t* info);
+
+/* C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C (all row-major). Exposed for tests/bench. */
+int pb_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+               int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
+               int32_t lower_only);
+
+/* ---- K3/K8: level-2 kernels -------------------------------------------------------------------
+ * pb_symv : y = K x for a full-storage symmetric K (Laplace.py:8,22; VB.py:9,23).
+ * pb_trsv : solve with the lower factor; trans=0: L x = rhs, trans=1: L^T x = rhs
+ *           (B.cholesky_solve at VB.py:11).  `rhs` is destroyed, `x` must not alias it;
+ *           `potrf_workspace` is the workspace pb_potrf filled (64x64 leaf inverses).
+ * pb_logdet_chol: out[0] = sum_i log L_ii (Laplace.py:28, VB.py:28).                              */
+int pb_symv(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x, double* y);
+int pb_trsv(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
+            int32_t trans, double* rhs, double* x);
+int pb_logdet_chol(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, double* out);
+
+/* X[m x n] <- X L^{-T} (right solve with the lower factor), the many-RHS form used by predict
+ * (replaces B.solve(K, Kfs) at approximators.py:177).  Uses the block inverses potrf left in
+ * `workspace`.                                                                                   */
+int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
+                     double* X, int64_t m, int64_t ldx);
+
+/* ---- A4-A9: fused fit drivers -----------------------------------------------------------------
+ * pb_laplace_fit: LaplaceGP.weight + precision (approximators.py:204-210,265-277) = Newton on
+ *   g(Kw) - w = 0 with jaxopt's stopping rule (solvers.py:7-25): w0 = 0; repeat w+ = Newton(w);
+ *   err = ||w+ - w||_2; until err <= tol or iters == maxiter.  Synchronises `stream` once per
+ *   iteration (8-byte readback of err).  Outputs: weight w (n), precision p = -h(Kw) (n),
+ *   posterior mean f = K w (n); when `final_factor` != 0 the workspace additionally ends holding
+ *   the Cholesky factor of B(w*) used by pb_laplace_objective / pb_predict.
+ * pb_vb_fit: VBGP.weight + precision (approximators.py:332-339; VB.py:4-16).                     */
+typedef struct pb_fit_result {
+    int32_t iterations;
+    int32_t info;       /* potrf info of the last factorisation (0 = ok) */
+    double error;       /* last ||w+ - w||_2 */
+    double sum_ll;      /* sum_i ll(f_i) at the returned w */
+    double ftw;         /* f^T w at the returned w */
+    double logdet;      /* sum log diag chol(...) of the final factor (if computed) */
+} pb_fit_result;
+
+typedef struct pb_problem {
+    const double* X;       /* (n, D) row-major training inputs (device) */
+    const void* y;         /* int64 labels or f64 targets (device) */
+    int64_t n;
+    int32_t D;
+    int32_t _pad;
+    pb_kernel_spec kernel;
+    pb_likelihood_spec lik;
+} pb_problem;
+
+/* Workspace layout is private; size it with pb_fit_workspace_bytes(n, D).  It holds K (n x ld),
+ * the factor buffer (n x ld), features and O(n) vectors. */
+int64_t pb_fit_workspace_bytes(int64_t n, int D);
+/* Build features + K(theta) into the workspace (what every fit does first); and locate K inside it. */
+int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
+int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk);
+int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
+                   double jitter, int32_t final_factor, void* workspace, int64_t workspace_bytes,
+                   double* weight, double* precision, double* posterior_mean, pb_fit_result* result_host);
+int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
+              void* workspace, int64_t workspace_bytes, double* weight, double* precision,
+              double* posterior_mean, pb_fit_result* result_host);
+
+/* ---- A10: predict -----------------------------------------------------------------------------
+ * Approximator.predict (approximators.py:154-180): mean = K_*f w,
+ * var = k_** - diag(K_*f (K + P^-1)^-1 K_f*) = k_** - || L_B^-1 (s o k_*) ||^2, s = sqrt(P).
+ * pb_predict_prepare builds K (skipped when reuse_gram != 0 and the workspace still holds K for
+ * these prior parameters) and factors B = I + s s^T o K into the workspace (one potrf);
+ * pb_predict then streams test points in chunks of `chunk` rows through a caller scratch buffer
+ * of pb_predict_scratch_bytes(n, chunk) (cross-covariance tiles are generated on the fly and
+ * never exist for more than one chunk).                                                         */
+int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, const double* precision,
+                       int32_t reuse_gram, void* workspace, int64_t workspace_bytes, int32_t* info_host);
+int64_t pb_predict_scratch_bytes(int64_t n, int D, int64_t chunk);
+int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace, const double* weight,
+               const double* X_test, int64_t n_test, int64_t chunk, void* scratch, int64_t scratch_bytes,
+               double* mean, double* variance);
+
+/* ---- K15: ordinal predictive distributions (probit/utilities.py:232-249) ----------------------
+ * out[n_test x J] = Phi((b[j+1]-m)/s) - Phi((b[j]-m)/s), s = sqrt(var + sigma^2).                */
+int pb_predictive_distributions(pb_stream_t stream, const pb_likelihood_spec* lik, const double* mean,
+                                const double* variance, int64_t n_test, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROBIT_B200_H */

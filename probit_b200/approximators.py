@@ -1,0 +1,287 @@
+"""LaplaceGP / VBGP with the reference's class API, running entirely on the B200 CUDA path.
+
+Mirrors probit/approximators.py: same constructor arguments, `approximate_posterior(parameters)`,
+`predict(X_test, parameters, weight, precision)`, `objective()`, `weight`, `precision`,
+`construct`.  `parameters = (prior_parameters, likelihood_parameters)` exactly as in the examples
+(examples/regression.py:139-143, examples/classification.py:414-417).  Arrays come back as
+torch.float64 CUDA tensors.
+
+What is recognised: `prior(prior_parameters)` must return a
+`probit_b200.kernels.Kernel` (or an mlkernels expression made of the same nodes) and
+`log_likelihood` must be `probit_b200.utilities.log_probit_likelihood` or
+`log_gaussian_likelihood`.  Anything else raises NotImplementedError: there is no CPU fallback.
+"""
+import ctypes as C
+import math
+from abc import ABC, abstractmethod
+
+import torch
+
+from . import _lib, kernels as _kernels, utilities as _util
+from .linalg import _dev, _mat2, _ptr, _stream
+
+
+def _likelihood_kind(log_likelihood, grad_log_likelihood, hessian_log_likelihood):
+    if log_likelihood is _util.log_gaussian_likelihood:
+        if grad_log_likelihood is not None or hessian_log_likelihood is not None:
+            raise NotImplementedError("custom derivatives of the Gaussian likelihood are not supported")
+        return _lib.PB_LIK_GAUSSIAN
+    if log_likelihood is _util.log_probit_likelihood:
+        safe_g = grad_log_likelihood is _util.grad_log_probit_likelihood
+        safe_h = hessian_log_likelihood is _util.hessian_log_probit_likelihood
+        if grad_log_likelihood is None and hessian_log_likelihood is None:
+            return _lib.PB_LIK_ORDINAL_PROBIT            # autodiff derivatives (approximators.py:92-95)
+        if safe_g and safe_h:
+            return _lib.PB_LIK_ORDINAL_PROBIT_SAFE        # examples/classification.py:406-407 (commented out there)
+        raise NotImplementedError("only the library's own grad/hessian_log_probit_likelihood pair is supported")
+    raise NotImplementedError(
+        "log_likelihood must be probit_b200.utilities.log_probit_likelihood or log_gaussian_likelihood; "
+        "arbitrary Python likelihoods cannot run on the CUDA path and there is no CPU fallback")
+
+
+class Approximator(ABC):
+    """probit/approximators.py:16-210."""
+
+    @abstractmethod
+    def __repr__(self):
+        ...
+
+    def __init__(self, data, prior, log_likelihood, grad_log_likelihood=None, hessian_log_likelihood=None,
+                 tolerance=1e-5, maxiter=100, jitter=1e-12, likelihood_eps=_util.LIKELIHOOD_EPS,
+                 predict_chunk=None):
+        self.tolerance = tolerance                      # approximators.py:90
+        self.maxiter = maxiter                          # jaxopt FixedPointIteration default
+        self.jitter = jitter                            # lab's B.epsilon in B.cholesky(Dense) (Laplace.py:24)
+        self.likelihood_eps = likelihood_eps
+        self.prior = prior
+        self.log_likelihood = log_likelihood
+        self._kind = _likelihood_kind(log_likelihood, grad_log_likelihood, hessian_log_likelihood)
+        self.lib = _lib.load()
+        X_train, y_train = data
+        self.X = _mat2(X_train)
+        (self.N, self.D) = self.X.shape                 # approximators.py:108
+        self.y = _util._labels(self._kind, y_train)
+        if self.y.numel() != self.N:
+            raise ValueError("X_train and y_train disagree on N")
+        self.data = (self.X, self.y)
+        self.predict_chunk = predict_chunk
+        self._ws = None
+        self._ws_bytes = 0
+        self._gram_key = None        # kernel spec bytes the workspace's K was built for
+        self._factor_key = None      # (spec bytes, precision clone) the workspace's factor was built for
+        self.last_result = None
+
+    # -- plumbing ---------------------------------------------------------------------------------
+    def _workspace(self):
+        if self._ws is None:
+            self._ws_bytes = self.lib.pb_fit_workspace_bytes(self.N, self.D)
+            self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device="cuda")
+        return self._ws
+
+    def _spec(self, prior_parameters):
+        kernel = _kernels.as_kernel(self.prior(prior_parameters))
+        return kernel.lower()
+
+    def _problem(self, parameters):
+        prior_parameters, likelihood_parameters = parameters
+        spec = self._spec(prior_parameters)
+        lik, keep = _util.make_likelihood_spec(self._kind, likelihood_parameters, self.likelihood_eps)
+        prob = _lib.Problem(self.X.data_ptr(), self.y.data_ptr(), self.N, self.D, 0, spec, lik)
+        return prob, keep
+
+    @staticmethod
+    def _spec_key(spec):
+        return bytes(spec)
+
+    def _ensure_gram(self, prob):
+        """Features + K(theta) in the workspace (for helpers such as `precision` / `posterior_mean`)."""
+        key = self._spec_key(prob.kernel)
+        ws = self._workspace()
+        if self._gram_key != key:
+            self._gram_key, self._factor_key = None, None
+            _lib.check(self.lib.pb_build_gram(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes))
+            self._gram_key = key
+        return ws
+
+    def _K_view(self):
+        """(N, N) view of the Gram matrix inside the workspace."""
+        ws = self._workspace()
+        Kp, ld = C.c_void_p(0), C.c_int64(0)
+        _lib.check(self.lib.pb_workspace_gram(_ptr(ws), self.N, self.D, C.byref(Kp), C.byref(ld)))
+        off = Kp.value - ws.data_ptr()
+        return ws[off: off + self.N * ld.value * 8].view(torch.float64).view(self.N, ld.value)[:, : self.N]
+
+    # -- reference API ----------------------------------------------------------------------------
+    @abstractmethod
+    def construct(self):
+        ...
+
+    @abstractmethod
+    def objective(self):
+        ...
+
+    @abstractmethod
+    def weight(self, parameters):
+        ...
+
+    @abstractmethod
+    def precision(self, weight, parameters):
+        ...
+
+    def posterior_mean(self, weight, parameters):
+        """K @ weight (approximators.py:199-202; the reference's version forgets its `parameters` argument)."""
+        prob, keep = self._problem(parameters)
+        self._ensure_gram(prob)
+        from . import linalg
+        return linalg.symv(self._K_view(), _dev(weight))
+
+    def predict(self, X_test, parameters, weight, precision):
+        """approximators.py:154-180: (mean, variance) of the latent GP at X_test, both (N_test,)."""
+        prob, keep = self._problem(parameters)
+        ws = self._workspace()
+        weight = _dev(weight).reshape(-1)
+        precision = _dev(precision).reshape(-1)
+        X_test = _mat2(X_test)
+        if X_test.shape[1] != self.D:
+            raise ValueError("X_test has the wrong input dimension")
+        key = self._spec_key(prob.kernel)
+        reuse_factor = (self._factor_key is not None and self._factor_key[0] == key
+                        and torch.equal(self._factor_key[1], precision))
+        if not reuse_factor:
+            info = C.c_int32(0)
+            reuse_gram = int(self._gram_key == key)
+            self._gram_key, self._factor_key = None, None
+            _lib.check(self.lib.pb_predict_prepare(_stream(), C.byref(prob), _ptr(precision), reuse_gram, _ptr(ws),
+                                                   self._ws_bytes, C.byref(info)))
+            self._gram_key, self._factor_key = key, (key, precision.clone())
+        n_test = X_test.shape[0]
+        chunk = self.predict_chunk or max(1, min(n_test, max(256, (1 << 31) // (8 * max(self.N, 1)))))
+        scratch_bytes = self.lib.pb_predict_scratch_bytes(self.N, self.D, chunk)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device="cuda")
+        mean = torch.empty(n_test, dtype=torch.float64, device="cuda")
+        var = torch.empty(n_test, dtype=torch.float64, device="cuda")
+        _lib.check(self.lib.pb_predict(_stream(), C.byref(prob), _ptr(ws), _ptr(weight), _ptr(X_test), n_test, chunk,
+                                       _ptr(scratch), scratch_bytes, _ptr(mean), _ptr(var)))
+        del keep
+        return mean, var
+
+    def approximate_posterior(self, parameters):
+        """approximators.py:204-210."""
+        w, p, _ = self._fit(parameters, final_factor=False)
+        return w, p
+
+
+class LaplaceGP(Approximator):
+    """probit/approximators.py:213-277 + probit/implicit/Laplace.py."""
+
+    def __repr__(self):
+        return "LaplaceGP"
+
+    def _fit(self, parameters, final_factor):
+        prob, keep = self._problem(parameters)
+        ws = self._workspace()
+        w = torch.empty(self.N, dtype=torch.float64, device="cuda")
+        p = torch.empty_like(w)
+        f = torch.empty_like(w)
+        res = _lib.FitResult()
+        self._gram_key, self._factor_key = None, None
+        status = self.lib.pb_laplace_fit(_stream(), C.byref(prob), float(self.tolerance), int(self.maxiter),
+                                         float(self.jitter), int(final_factor), _ptr(ws), self._ws_bytes, _ptr(w),
+                                         _ptr(p), _ptr(f), C.byref(res))
+        self.last_result = res
+        _lib.check(status)
+        self._gram_key = self._spec_key(prob.kernel)
+        del keep
+        return w, p, f
+
+    def construct(self):
+        """approximators.py:238-246: (parameters, weight) -> f_LA = grad_ll(K w) (Laplace.py:4-9)."""
+        def f(parameters, weight):
+            m = self.posterior_mean(weight, parameters)
+            return _util.evaluate_likelihood(self._kind, m, self.y, parameters[1], ("g",), self.likelihood_eps)["g"]
+        return f
+
+    def weight(self, parameters):
+        """approximators.py:265-269."""
+        return self._fit(parameters, final_factor=False)[0]
+
+    def precision(self, weight, parameters):
+        """approximators.py:271-277: (-hessian_ll(K w), K w)."""
+        m = self.posterior_mean(weight, parameters)
+        h = _util.evaluate_likelihood(self._kind, m, self.y, parameters[1], ("h",), self.likelihood_eps)["h"]
+        return -h, m
+
+    def objective(self):
+        """approximators.py:248-263 -> objective_LA (Laplace.py:12-30): negative Laplace evidence.
+
+        -sum ll(f) + 0.5 f^T w + sum log diag chol(K + P^-1 + jitter I) + 0.5 sum log p, the last two
+        terms evaluated as sum log diag chol(I + P^1/2 (K + jitter I) P^1/2).
+        """
+        def obj(parameters):
+            self._fit(parameters, final_factor=True)
+            r = self.last_result
+            return -r.sum_ll + 0.5 * r.ftw + r.logdet
+        return obj
+
+
+class VBGP(Approximator):
+    """probit/approximators.py:280-339 + probit/implicit/VB.py."""
+
+    def __repr__(self):
+        return "VBGP"
+
+    def _fit(self, parameters, final_factor):
+        prob, keep = self._problem(parameters)
+        ws = self._workspace()
+        w = torch.empty(self.N, dtype=torch.float64, device="cuda")
+        p = torch.empty_like(w)
+        f = torch.empty_like(w)
+        res = _lib.FitResult()
+        self._gram_key, self._factor_key = None, None
+        status = self.lib.pb_vb_fit(_stream(), C.byref(prob), float(self.tolerance), int(self.maxiter), _ptr(ws),
+                                    self._ws_bytes, _ptr(w), _ptr(p), _ptr(f), C.byref(res))
+        self.last_result = res
+        _lib.check(status)
+        self._gram_key = self._spec_key(prob.kernel)
+        del keep
+        return w, p, f
+
+    def construct(self):
+        """approximators.py:306-314: (parameters, weight) -> f_VB (VB.py:4-16)."""
+        def f(parameters, weight):
+            from . import linalg
+            prob, keep = self._problem(parameters)
+            self._ensure_gram(prob)
+            sigma = float(parameters[1][0])
+            K = self._K_view()
+            m = linalg.symv(K, _dev(weight))
+            g = _util.evaluate_likelihood(self._kind, m, self.y, parameters[1], ("g",), self.likelihood_eps)["g"]
+            A = linalg.empty_matrix(self.N, self.N)
+            _lib.check(self.lib.pb_copy_lower_add_diag(_stream(), _ptr(K), self.N, K.stride(0), sigma * sigma,
+                                                       _ptr(A), A.stride(0)))
+            return linalg.cholesky_solve(linalg.potrf_(A), m + sigma * g)
+        return f
+
+    def weight(self, parameters):
+        """approximators.py:332-334."""
+        return self._fit(parameters, final_factor=False)[0]
+
+    def precision(self, weight, parameters):
+        """approximators.py:336-339."""
+        m = self.posterior_mean(weight, parameters)
+        sigma = float(parameters[1][0])
+        return torch.full_like(m, 1.0 / sigma**2), m
+
+    def objective(self):
+        """approximators.py:316-330 -> objective_VB (VB.py:19-40): negative ELBO.
+
+        The reference forms C = (sigma^2 I + K)^-1 explicitly; since K C = I - sigma^2 C the two trace
+        terms sum to N/2 and cancel the -N/2, leaving
+        0.5 f^T w - N log sigma + sum log diag L - sum ll(f)   (SURVEY.md §8a row A9).
+        """
+        def obj(parameters):
+            self._fit(parameters, final_factor=True)
+            r = self.last_result
+            sigma = float(parameters[1][0])
+            return 0.5 * r.ftw - self.N * math.log(sigma) + r.logdet - r.sum_ll
+        return obj

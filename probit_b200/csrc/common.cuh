@@ -1,0 +1,111 @@
+// Shared helpers for the probit_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cmath>
+#include "../../include/probit_b200.h"
+
+namespace pb {
+
+// thread-local message behind pb_last_error()
+void set_error(const char* fmt, ...);
+
+#define PB_CUDA(expr)                                                                         \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            pb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return PB_ERR_CUDA;                                                               \
+        }                                                                                     \
+    } while (0)
+
+#define PB_CHECK(cond, code, ...)                                                             \
+    do {                                                                                      \
+        if (!(cond)) {                                                                        \
+            pb::set_error(__VA_ARGS__);                                                       \
+            return (code);                                                                    \
+        }                                                                                     \
+    } while (0)
+
+#define PB_TRY(expr)                                                                          \
+    do {                                                                                      \
+        int _s = (expr);                                                                      \
+        if (_s != PB_OK) return _s;                                                           \
+    } while (0)
+
+inline int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0 (and broadcast to all through smem)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double red[THREADS / 32];
+    __shared__ double total;
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double x = threadIdx.x < THREADS / 32 ? red[threadIdx.x] : 0.0;
+        x = warp_sum(x);
+        if (threadIdx.x == 0) total = x;
+    }
+    __syncthreads();
+    return total;
+}
+
+// ---- internal entry points shared between translation units (all enqueue on `stream`) ----
+
+// C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C, all row-major (K contiguous for A and B).
+// lower_only: skip tiles strictly above the diagonal and mask the upper part of diagonal tiles
+// (M == N required).  Pointers 16-byte aligned, leading dimensions even.
+int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only);
+
+// potrf.cu
+int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
+          int32_t* info);
+int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
+                  double* X, int64_t m, int64_t ldx);
+
+// gram.cu
+int feature_dim(const pb_kernel_spec& spec, int D);
+int features(cudaStream_t stream, const pb_kernel_spec& spec, const double* X, int64_t n, int D, int64_t ldx,
+             double* Z, int64_t ldz);
+int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+             double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
+int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
+               int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale);
+int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, const double* s, double a,
+                  double jitter, double* B, int64_t ldb);
+
+// blas2.cu
+int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y);
+int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const double* dinv, bool trans, double* rhs,
+         double* x);
+int logdet_chol(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* out);
+
+// likelihood.cu
+int likelihood(cudaStream_t stream, const pb_likelihood_spec& spec, const double* f, const void* y, int64_t n,
+               int64_t batch, double* ll, double* g, double* h, double* d3);
+
+}  // namespace pb

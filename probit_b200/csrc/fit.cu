@@ -1,0 +1,513 @@
+// Fused fit / predict drivers: the host side of the hot path, below the C ABI.
+//
+//  pb_laplace_fit   LaplaceGP.weight + precision  (probit/approximators.py:204-210,265-277;
+//                   f_LA probit/implicit/Laplace.py:4-9; newton_solver + fwd_solver
+//                   probit/implicit/solvers.py:7-25 with jaxopt's stopping rule)
+//  pb_vb_fit        VBGP.weight + precision       (approximators.py:332-339; f_VB VB.py:4-16)
+//  pb_predict*      Approximator.predict          (approximators.py:154-180)
+//
+// Newton step.  The reference forms J = diag(h) K - I densely (2N^3 flops through jax.jacobian)
+// and LU-solves it ((2/3)N^3).  With W = -h >= 0, s = sqrt(W), b = W f + g, B = I + s s^T o K:
+//     w+ = w - J^{-1}(g - w) = (I + W K)^{-1} b = b - s o B^{-1} (s o (K b))
+// (Rasmussen & Williams Alg. 3.1), which needs one Cholesky of the SPD, well-conditioned B
+// (N^3/3 flops) and never divides by W.  The iterates agree with the LU form to ~1e-14
+// (tests/test_oracle_fit.py) and the iteration count is identical.
+#include "likelihood.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int VEC_BLOCKS_MAX = 1024;
+
+inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+struct Layout {
+    int64_t n, ld;
+    int Dfmax;
+    // byte offsets
+    int64_t K, B, Z, potrf_ws, vec, partial, scalars, info, total;
+    int64_t vec_stride;   // doubles per vector slot
+};
+
+enum VecSlot { V_W = 0, V_WN, V_F, V_S, V_B, V_T, V_C, V_X, V_G, V_COUNT };
+enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_COUNT = 8 };
+
+Layout make_layout(int64_t n, int D) {
+    Layout L;
+    L.n = n;
+    L.ld = round_up(n > 0 ? n : 1, 16);
+    L.Dfmax = 2 * D;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
+    L.K = take(n * L.ld * 8);
+    L.B = take(n * L.ld * 8);
+    L.Z = take(n * (int64_t)L.Dfmax * 8);
+    L.potrf_ws = take(pb_potrf_workspace_bytes(n));
+    L.vec_stride = round_up(n > 0 ? n : 1, 32);
+    L.vec = take(L.vec_stride * V_COUNT * 8);
+    L.partial = take(VEC_BLOCKS_MAX * 2 * 8);
+    L.scalars = take(S_COUNT * 8);
+    L.info = take(256);
+    L.total = off;
+    return L;
+}
+
+struct Ws {
+    Layout L;
+    uint8_t* base;
+    double* K() const { return reinterpret_cast<double*>(base + L.K); }
+    double* B() const { return reinterpret_cast<double*>(base + L.B); }
+    double* Z() const { return reinterpret_cast<double*>(base + L.Z); }
+    void* potrf_ws() const { return base + L.potrf_ws; }
+    double* dinv() const { return reinterpret_cast<double*>(base + L.potrf_ws); }
+    double* vec(int slot) const { return reinterpret_cast<double*>(base + L.vec) + slot * L.vec_stride; }
+    double* partial() const { return reinterpret_cast<double*>(base + L.partial); }
+    double* scalars() const { return reinterpret_cast<double*>(base + L.scalars); }
+    int32_t* info() const { return reinterpret_cast<int32_t*>(base + L.info); }
+};
+
+inline unsigned vec_blocks(int64_t n) {
+    int64_t b = ceil_div<int64_t>(n, 256);
+    return (unsigned)(b < 1 ? 1 : (b > VEC_BLOCKS_MAX ? VEC_BLOCKS_MAX : b));
+}
+
+// two partial sums per block -> partial[2*block + k]
+__device__ __forceinline__ void write_partials(double a, double b, double* partial) {
+    a = block_sum<256>(a);
+    b = block_sum<256>(b);
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = a;
+        partial[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(const double* __restrict__ partial, int nblk, double* out0, double* out1) {
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < nblk; i += 256) {
+        a += partial[2 * i];
+        b += partial[2 * i + 1];
+    }
+    a = block_sum<256>(a);
+    b = block_sum<256>(b);
+    if (threadIdx.x == 0) {
+        if (out0) *out0 = a;
+        if (out1) *out1 = b;
+    }
+}
+
+// Newton prep (Laplace.py:4-9 + its derivative): s = sqrt(W), b = W f + g with W = -h.
+// partials: sum ll, number of data with W < 0 or NaN.
+__global__ void __launch_bounds__(256)
+laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
+                    const void* __restrict__ y, int64_t n, double* __restrict__ s, double* __restrict__ b,
+                    double* __restrict__ partial) {
+    __shared__ double sc[lik::MAX_CUT + 1];
+    lik::stage_cutpoints(p, cut, sc);
+    double sum_ll = 0, bad = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double fi = f[i];
+        const lik::Out o = lik::eval(p, fi, y, i, sc);
+        const double W = -o.h;
+        if (!(W >= 0.0)) bad += 1.0;
+        s[i] = sqrt(W);
+        b[i] = fma(W, fi, o.g);
+        sum_ll += o.ll;
+    }
+    write_partials(sum_ll, bad, partial);
+}
+
+// precision p = -h(f) (approximators.py:274-276); partials: sum ll(f), f.w
+__global__ void __launch_bounds__(256)
+posterior_stats_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
+                       const void* __restrict__ y, const double* __restrict__ w, int64_t n, double* __restrict__ prec,
+                       double* __restrict__ partial) {
+    __shared__ double sc[lik::MAX_CUT + 1];
+    lik::stage_cutpoints(p, cut, sc);
+    double sum_ll = 0, ftw = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double fi = f[i];
+        const lik::Out o = lik::eval(p, fi, y, i, sc);
+        if (prec) prec[i] = -o.h;
+        sum_ll += o.ll;
+        ftw = fma(fi, w[i], ftw);
+    }
+    write_partials(sum_ll, ftw, partial);
+}
+
+// VB right-hand side (VB.py:11-15): r = f + sigma * g(f)
+__global__ void __launch_bounds__(256)
+vb_rhs_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f, const void* __restrict__ y,
+              int64_t n, double* __restrict__ r) {
+    __shared__ double sc[lik::MAX_CUT + 1];
+    lik::stage_cutpoints(p, cut, sc);
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double fi = f[i];
+        const lik::Out o = lik::eval(p, fi, y, i, sc);
+        r[i] = fma(p.sigma, o.g, fi);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+mul_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = a[i] * b[i];
+}
+
+__global__ void __launch_bounds__(256)
+sqrt_kernel(const double* __restrict__ a, int64_t n, double* __restrict__ out, double* __restrict__ partial) {
+    double bad = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = a[i];
+        if (!(v >= 0.0)) bad += 1.0;
+        out[i] = sqrt(v);
+    }
+    write_partials(0.0, bad, partial);
+}
+
+__global__ void __launch_bounds__(256)
+fill_kernel(double* __restrict__ a, int64_t n, double v) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) a[i] = v;
+}
+
+// w+ = b - s o c ; partial: ||w+ - w||^2   (solvers.py:24 + jaxopt's error)
+__global__ void __launch_bounds__(256)
+newton_update_kernel(const double* __restrict__ b, const double* __restrict__ s, const double* __restrict__ c,
+                     const double* __restrict__ w, int64_t n, double* __restrict__ wn, double* __restrict__ partial) {
+    double e2 = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = fma(-s[i], c[i], b[i]);
+        const double d = v - w[i];
+        e2 = fma(d, d, e2);
+        wn[i] = v;
+    }
+    write_partials(e2, 0.0, partial);
+}
+
+__global__ void __launch_bounds__(256)
+diff_norm_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ partial) {
+    double e2 = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double d = a[i] - b[i];
+        e2 = fma(d, d, e2);
+    }
+    write_partials(e2, 0.0, partial);
+}
+
+// var[i] = kss - sum_j V[i][j]^2 ; one warp per row
+__global__ void __launch_bounds__(256)
+row_sumsq_kernel(const double* __restrict__ V, int64_t rows, int64_t cols, int64_t ld, double kss,
+                 double* __restrict__ var) {
+    const int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* p = V + r * ld;
+    double s = 0;
+    const int64_t c2 = cols >> 1;
+    for (int64_t j = lane; j < c2; j += 32) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(p) + j);
+        s = fma(v.x, v.x, s);
+        s = fma(v.y, v.y, s);
+    }
+    if ((cols & 1) && lane == 0) s = fma(p[cols - 1], p[cols - 1], s);
+    s = warp_sum(s);
+    if (lane == 0) var[r] = kss - s;
+}
+
+int check_problem(const pb_problem* prob) {
+    PB_CHECK(prob != nullptr, PB_ERR_INVALID, "null problem");
+    PB_CHECK(prob->n >= 1 && prob->D >= 1, PB_ERR_INVALID, "problem needs n >= 1 and D >= 1");
+    PB_CHECK(prob->X != nullptr && prob->y != nullptr, PB_ERR_INVALID, "problem data missing");
+    return PB_OK;
+}
+
+int bind(const pb_problem* prob, void* workspace, int64_t workspace_bytes, Ws& ws) {
+    PB_TRY(check_problem(prob));
+    ws.L = make_layout(prob->n, prob->D);
+    PB_CHECK(workspace != nullptr && workspace_bytes >= ws.L.total, PB_ERR_INVALID,
+             "workspace too small: need %lld bytes, got %lld", (long long)ws.L.total, (long long)workspace_bytes);
+    PB_CHECK((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, PB_ERR_INVALID, "workspace must be 256-byte aligned");
+    ws.base = reinterpret_cast<uint8_t*>(workspace);
+    return PB_OK;
+}
+
+int build_gram(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
+    const int Df = feature_dim(prob->kernel, prob->D);
+    PB_TRY(features(st, prob->kernel, prob->X, prob->n, prob->D, prob->D, ws.Z(), Df));
+    return gram_sym(st, prob->kernel, ws.Z(), prob->n, Df, Df, ws.K(), ws.L.ld, nullptr, 0.0);
+}
+
+int finalize(cudaStream_t st, const Ws& ws, unsigned nblk, double* out0, double* out1) {
+    finalize_kernel<<<1, 256, 0, st>>>(ws.partial(), (int)nblk, out0, out1);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int read_scalars(cudaStream_t st, const Ws& ws, double* host, int32_t* info_host) {
+    PB_CUDA(cudaMemcpyAsync(host, ws.scalars(), S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (info_host) PB_CUDA(cudaMemcpyAsync(info_host, ws.info(), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    return PB_OK;
+}
+
+// posterior mean f = K w, precision, sum ll, f.w  -> device scalars
+int posterior_stats(cudaStream_t st, const pb_problem* prob, const lik::Params& lp, const Ws& ws, const double* w,
+                    double* prec_out) {
+    const int64_t n = prob->n;
+    PB_TRY(gemv(st, ws.K(), n, n, ws.L.ld, w, ws.vec(V_F)));
+    const unsigned nb = vec_blocks(n);
+    posterior_stats_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, w, n, prec_out,
+                                               ws.partial());
+    PB_CUDA(cudaGetLastError());
+    return finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_FTW);
+}
+
+// B = I + s s^T o (K + jitter I), factor in place, logdet -> device scalar
+int factor_B(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double jitter) {
+    PB_TRY(sym_transform(st, ws.K(), n, ws.L.ld, s, 1.0, jitter, ws.B(), ws.L.ld));
+    PB_TRY(potrf(st, ws.B(), n, ws.L.ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info()));
+    return logdet_chol(st, ws.B(), n, ws.L.ld, ws.scalars() + S_LOGDET);
+}
+
+}  // namespace
+}  // namespace pb
+
+using namespace pb;
+
+extern "C" int64_t pb_fit_workspace_bytes(int64_t n, int D) { return make_layout(n, D).total; }
+
+extern "C" int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes) {
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    return build_gram(reinterpret_cast<cudaStream_t>(stream), prob, ws);
+}
+
+extern "C" int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk) {
+    PB_CHECK(workspace && K && ldk, PB_ERR_INVALID, "workspace_gram: null argument");
+    const Layout L = make_layout(n, D);
+    *K = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(workspace) + L.K);
+    *ldk = L.ld;
+    return PB_OK;
+}
+
+extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
+                              double jitter, int32_t final_factor, void* workspace, int64_t workspace_bytes,
+                              double* weight, double* precision, double* posterior_mean,
+                              pb_fit_result* result_host) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    PB_CHECK(weight && precision && result_host, PB_ERR_INVALID, "laplace_fit: null output");
+    lik::Params lp;
+    PB_TRY(lik::make_params(prob->lik, lp));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const unsigned nb = vec_blocks(n);
+    *result_host = pb_fit_result{};
+
+    PB_TRY(build_gram(st, prob, ws));
+    PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    PB_CUDA(cudaMemsetAsync(ws.vec(V_W), 0, n * sizeof(double), st));       // z_init = zeros (approximators.py:268)
+
+    double host[S_COUNT];
+    int32_t info_host = 0;
+    double error = INFINITY;
+    int it = 0;
+    double* w = ws.vec(V_W);
+    double* wn = ws.vec(V_WN);
+    while (error > tolerance && it < maxiter) {                             // jaxopt loop (solvers.py:13-14)
+        if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
+        else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
+        laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_S),
+                                                ws.vec(V_B), ws.partial());
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
+        PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));
+        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));       // K b
+        mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C));
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
+        newton_update_kernel<<<nb, 256, 0, st>>>(ws.vec(V_B), ws.vec(V_S), ws.vec(V_C), w, n, wn, ws.partial());
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, ws.scalars() + S_ERR2, nullptr));
+        PB_TRY(read_scalars(st, ws, host, &info_host));
+        ++it;
+        result_host->iterations = it;
+        result_host->info = info_host;
+        if (host[S_BAD] > 0) {
+            set_error("laplace_fit: %d data have negative or NaN likelihood curvature at iteration %d; the SPD "
+                      "Newton form needs W = -h >= 0", (int)host[S_BAD], it);
+            return PB_ERR_NUMERIC;
+        }
+        if (info_host != 0) {
+            set_error("laplace_fit: Cholesky of I + W^1/2 K W^1/2 failed at column %d (iteration %d)", info_host, it);
+            return PB_ERR_NUMERIC;
+        }
+        error = sqrt(host[S_ERR2]);
+        result_host->error = error;
+        if (!(error == error)) {
+            set_error("laplace_fit: NaN iterate at iteration %d", it);
+            return PB_ERR_NUMERIC;
+        }
+        double* tmp = w; w = wn; wn = tmp;
+    }
+    // LaplaceGP.precision (approximators.py:271-277) at the returned weight
+    PB_TRY(posterior_stats(st, prob, lp, ws, w, precision));
+    PB_CUDA(cudaMemcpyAsync(weight, w, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (posterior_mean)
+        PB_CUDA(cudaMemcpyAsync(posterior_mean, ws.vec(V_F), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (final_factor) {
+        // chol(K + diag(1/p) + jitter I) of objective_LA (Laplace.py:24) in its B form:
+        // sum log diag L_cov + 0.5 sum log p == sum log diag chol(I + s s^T o (K + jitter I))
+        const unsigned nb2 = vec_blocks(n);
+        sqrt_kernel<<<nb2, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial());
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb2, nullptr, ws.scalars() + S_BAD));
+        PB_TRY(factor_B(st, ws, n, ws.vec(V_S), jitter));
+    }
+    PB_TRY(read_scalars(st, ws, host, &info_host));
+    result_host->sum_ll = host[S_SUMLL];
+    result_host->ftw = host[S_FTW];
+    result_host->logdet = final_factor ? host[S_LOGDET] : NAN;
+    result_host->info = info_host;
+    if (final_factor && (host[S_BAD] > 0 || info_host != 0)) {
+        set_error("laplace_fit: final factorisation failed (bad precisions %d, potrf info %d)", (int)host[S_BAD],
+                  info_host);
+        return PB_ERR_NUMERIC;
+    }
+    return PB_OK;
+}
+
+extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
+                         void* workspace, int64_t workspace_bytes, double* weight, double* precision,
+                         double* posterior_mean, pb_fit_result* result_host) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    PB_CHECK(weight && precision && result_host, PB_ERR_INVALID, "vb_fit: null output");
+    lik::Params lp;
+    PB_TRY(lik::make_params(prob->lik, lp));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const unsigned nb = vec_blocks(n);
+    *result_host = pb_fit_result{};
+    const double sigma = prob->lik.sigma;
+
+    PB_TRY(build_gram(st, prob, ws));
+    PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    // L = chol(sigma^2 I + K) (VB.py:10) — loop invariant, factored once (no jitter: raw-array path)
+    PB_TRY(sym_transform(st, ws.K(), n, ld, nullptr, sigma * sigma, 0.0, ws.B(), ld));
+    PB_TRY(potrf(st, ws.B(), n, ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info()));
+    PB_TRY(logdet_chol(st, ws.B(), n, ld, ws.scalars() + S_LOGDET));
+    PB_CUDA(cudaMemsetAsync(ws.vec(V_W), 0, n * sizeof(double), st));
+
+    double host[S_COUNT];
+    int32_t info_host = 0;
+    PB_TRY(read_scalars(st, ws, host, &info_host));
+    result_host->info = info_host;
+    if (info_host != 0) {
+        set_error("vb_fit: Cholesky of sigma^2 I + K failed at column %d", info_host);
+        return PB_ERR_NUMERIC;
+    }
+    double error = INFINITY;
+    int it = 0;
+    double* w = ws.vec(V_W);
+    double* wn = ws.vec(V_WN);
+    while (error > tolerance && it < maxiter) {
+        if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));
+        else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
+        vb_rhs_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_B));
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_B), ws.vec(V_X)));     // cholesky_solve (VB.py:11)
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), wn));
+        diff_norm_kernel<<<nb, 256, 0, st>>>(wn, w, n, ws.partial());
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, ws.scalars() + S_ERR2, nullptr));
+        PB_TRY(read_scalars(st, ws, host, nullptr));
+        ++it;
+        error = sqrt(host[S_ERR2]);
+        result_host->iterations = it;
+        result_host->error = error;
+        if (!(error == error)) {
+            set_error("vb_fit: NaN iterate at iteration %d", it);
+            return PB_ERR_NUMERIC;
+        }
+        double* tmp = w; w = wn; wn = tmp;
+    }
+    PB_TRY(posterior_stats(st, prob, lp, ws, w, nullptr));
+    fill_kernel<<<nb, 256, 0, st>>>(precision, n, 1.0 / (sigma * sigma));     // approximators.py:339
+    PB_CUDA(cudaMemcpyAsync(weight, w, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (posterior_mean)
+        PB_CUDA(cudaMemcpyAsync(posterior_mean, ws.vec(V_F), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PB_TRY(read_scalars(st, ws, host, nullptr));
+    result_host->sum_ll = host[S_SUMLL];
+    result_host->ftw = host[S_FTW];
+    result_host->logdet = host[S_LOGDET];
+    return PB_OK;
+}
+
+extern "C" int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, const double* precision,
+                                  int32_t reuse_gram, void* workspace, int64_t workspace_bytes,
+                                  int32_t* info_host) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    PB_CHECK(precision != nullptr && info_host != nullptr, PB_ERR_INVALID, "predict_prepare: null argument");
+    const int64_t n = prob->n;
+    if (!reuse_gram) PB_TRY(build_gram(st, prob, ws));
+    PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    const unsigned nb = vec_blocks(n);
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial());
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, nullptr, ws.scalars() + S_BAD));
+    PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));       // K + diag(1/p) (approximators.py:175) in B form
+    double host[S_COUNT];
+    PB_TRY(read_scalars(st, ws, host, info_host));
+    if (host[S_BAD] > 0) {
+        set_error("predict_prepare: %d precisions are negative or NaN", (int)host[S_BAD]);
+        return PB_ERR_NUMERIC;
+    }
+    if (*info_host != 0) {
+        set_error("predict_prepare: Cholesky failed at column %d", *info_host);
+        return PB_ERR_NUMERIC;
+    }
+    return PB_OK;
+}
+
+extern "C" int64_t pb_predict_scratch_bytes(int64_t n, int D, int64_t chunk) {
+    const int64_t ld = round_up(n > 0 ? n : 1, 16);
+    return round_up(chunk * ld * 8, 256) + round_up(chunk * 2 * (int64_t)D * 8, 256) + 256;
+}
+
+extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace, const double* weight,
+                          const double* X_test, int64_t n_test, int64_t chunk, void* scratch,
+                          int64_t scratch_bytes, double* mean, double* variance) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    PB_TRY(check_problem(prob));
+    PB_CHECK(workspace != nullptr && weight != nullptr && mean != nullptr, PB_ERR_INVALID, "predict: null argument");
+    PB_CHECK(n_test >= 0 && chunk >= 1, PB_ERR_INVALID, "predict: bad n_test/chunk");
+    PB_CHECK(scratch != nullptr && scratch_bytes >= pb_predict_scratch_bytes(prob->n, prob->D, chunk), PB_ERR_INVALID,
+             "predict: scratch too small");
+    PB_CHECK((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, PB_ERR_INVALID, "predict: scratch must be 256-byte aligned");
+    Ws ws;
+    ws.L = make_layout(prob->n, prob->D);
+    ws.base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(workspace));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const int D = prob->D, Df = feature_dim(prob->kernel, D);
+    double* V = reinterpret_cast<double*>(scratch);
+    double* Zs = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + round_up(chunk * ld * 8, 256));
+    const double kss = prob->kernel.scale;    // kernel.elwise(x*, x*) of a stationary kernel (approximators.py:172)
+    for (int64_t r0 = 0; r0 < n_test; r0 += chunk) {
+        const int64_t m = n_test - r0 < chunk ? n_test - r0 : chunk;
+        PB_TRY(features(st, prob->kernel, X_test + r0 * D, m, D, D, Zs, Df));
+        // K_*f tile (approximators.py:173, transposed: test points are rows)
+        PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, Df, Df, V, ld, nullptr));
+        PB_TRY(gemv(st, V, m, n, ld, weight, mean + r0));                                   // approximators.py:179
+        if (variance) {
+            // var = k** - || L_B^{-1} (s o k_*) ||^2  ==  Kss - einsum(Kfs, solve(K + P^-1, Kfs)) (approximators.py:175-178)
+            PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, Df, Df, V, ld, ws.vec(V_S)));
+            PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), V, m, ld));
+            row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, st>>>(V, m, n, ld, kss, variance + r0);
+            PB_CUDA(cudaGetLastError());
+        }
+    }
+    return PB_OK;
+}

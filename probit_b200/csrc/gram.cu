@@ -1,0 +1,354 @@
+// Fused Gram-matrix assembly for the mlkernels priors the reference examples use
+// (EQ, Matern12/Exp, stretch, periodic, scalar scale).
+//
+// Replaces `prior(theta)(X)` at probit/implicit/Laplace.py:7,21,24, VB.py:7,22,
+// probit/approximators.py:174,272,337 and `kernel(X_train, X_test)` at approximators.py:173.
+//
+//  1. pb_features maps inputs once: Z = T(X / stretch_in) / stretch_out (T = periodic sin/cos
+//     feature map or identity), so the N^2 loop contains no trigonometry.
+//  2. gram kernels evaluate r^2 = sum_d (z_id - z_jd)^2 with exact differences (no GEMM expansion:
+//     SURVEY.md §7.2(b) — the expansion form puts O(1e-8) noise on diag(K) for Matern12) in 64x64
+//     tiles, 4x4 outputs per thread, features staged in shared memory, 256-byte coalesced row
+//     stores.  The symmetric variant computes lower tiles only and mirror-stores the transposed
+//     tile through shared memory, so it is bound by the 8*N^2-byte HBM write, not by FP64 exp.
+#include "common.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int MAX_DF = 64;
+constexpr double TWO_PI = 6.283185307179586;
+
+__global__ void __launch_bounds__(256)
+features_kernel(const double* __restrict__ X, int64_t n, int D, int64_t ldx, double* __restrict__ Z, int64_t ldz,
+                int periodic, double stretch_in, double period, double stretch_out) {
+    const int64_t total = n * D;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / D;
+        const int d = (int)(e % D);
+        double u = X[i * ldx + d];
+        if (stretch_in != 1.0) u = u / stretch_in;
+        if (periodic) {
+            const double a = TWO_PI * u / period;
+            double s, c;
+            sincos(a, &s, &c);
+            Z[i * ldz + d] = s / stretch_out;
+            Z[i * ldz + D + d] = c / stretch_out;
+        } else {
+            Z[i * ldz + d] = u / stretch_out;
+        }
+    }
+}
+
+__device__ __forceinline__ double base_eval(int base, double scale, double r2) {
+    return base == PB_BASE_EQ ? scale * exp(-0.5 * r2) : scale * exp(-sqrt(r2));
+}
+
+// Loads the features of 64 rows starting at row0 into s[d*64 + r] (zero beyond n).
+__device__ __forceinline__ void stage_features(double* s, const double* __restrict__ Z, int64_t ldz, int64_t row0,
+                                               int64_t n, int Df) {
+    for (int e = threadIdx.x; e < TILE * Df; e += 256) {
+        const int r = e / Df, d = e % Df;
+        const int64_t i = row0 + r;
+        s[d * TILE + r] = i < n ? Z[i * ldz + d] : 0.0;
+    }
+}
+
+// thread (ty, tx): rows ty + 16*r, cols 2*tx + 32*c + e
+__device__ __forceinline__ void tile_distances(const double* si, const double* sj, int Df, int ty, int tx,
+                                               double (&acc)[4][4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int d = 0; d < Df; ++d) {
+        double zi[4], zj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) zi[r] = si[d * TILE + ty + 16 * r];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const double2 v = *reinterpret_cast<const double2*>(&sj[d * TILE + 2 * tx + 32 * c]);
+            zj[2 * c] = v.x;
+            zj[2 * c + 1] = v.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double diff = zi[r] - zj[c];
+                acc[r][c] = fma(diff, diff, acc[r][c]);
+            }
+    }
+}
+
+// Lower-triangular tile enumeration: block b -> (ti, tj), tj <= ti.
+__device__ __forceinline__ void tri_tile(int64_t b, int& ti, int& tj) {
+    int64_t r = (int64_t)((sqrt(8.0 * (double)b + 1.0) - 1.0) * 0.5);
+    while ((r + 1) * (r + 2) / 2 <= b) ++r;
+    while (r * (r + 1) / 2 > b) --r;
+    ti = (int)r;
+    tj = (int)(b - r * (r + 1) / 2);
+}
+
+__global__ void __launch_bounds__(256)
+gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, double* __restrict__ K, int64_t ldk,
+                int base, double scale, const double* __restrict__ diag_vec, double diag_scalar) {
+    extern __shared__ __align__(16) double sm[];
+    double* si = sm;                   // [Df][64]
+    double* sj = sm + Df * TILE;       // [Df][64]
+    double* T = sj + Df * TILE;        // [64][65] transposed staging
+    int ti, tj;
+    tri_tile(blockIdx.x, ti, tj);
+    const int64_t i0 = (int64_t)ti * TILE, j0 = (int64_t)tj * TILE;
+    stage_features(si, Z, ldz, i0, n, Df);
+    stage_features(sj, Z, ldz, j0, n, Df);
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+    tile_distances(si, sj, Df, ty, tx, acc);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = base_eval(base, scale, acc[r][c]);
+
+    const bool diag_tile = ti == tj;
+    if (diag_tile) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int row = ty + 16 * r, col = 2 * tx + 32 * (c >> 1) + (c & 1);
+                if (row == col && i0 + row < n)
+                    acc[r][c] += diag_scalar + (diag_vec ? diag_vec[i0 + row] : 0.0);
+            }
+    }
+    const bool full_cols = (j0 + TILE <= n) && ((ldk & 1) == 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = i0 + ty + 16 * r;
+        if (row >= n) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int64_t col = j0 + 2 * tx + 32 * c;
+            double* p = K + row * ldk + col;
+            if (full_cols) {
+                *reinterpret_cast<double2*>(p) = make_double2(acc[r][2 * c], acc[r][2 * c + 1]);
+            } else {
+                if (col < n) p[0] = acc[r][2 * c];
+                if (col + 1 < n) p[1] = acc[r][2 * c + 1];
+            }
+        }
+    }
+    if (diag_tile) return;
+    // mirror: K[j0 + col][i0 + row] = acc(row, col), transposed through smem for coalesced rows
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (TILE + 1) + ty + 16 * r] = acc[r][c];
+    __syncthreads();
+    const bool full_rows = (i0 + TILE <= n) && ((ldk & 1) == 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = j0 + ty + 16 * r;      // always < n because tj < ti
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int lc = 2 * tx + 32 * c;
+            const int64_t col = i0 + lc;
+            const double v0 = T[(ty + 16 * r) * (TILE + 1) + lc], v1 = T[(ty + 16 * r) * (TILE + 1) + lc + 1];
+            double* p = K + row * ldk + col;
+            if (full_rows) {
+                *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+            } else {
+                if (col < n) p[0] = v0;
+                if (col + 1 < n) p[1] = v1;
+            }
+        }
+    }
+}
+
+// K[n1 x n2] = k(Z1, Z2) * (col_scale ? col_scale[j] : 1)
+__global__ void __launch_bounds__(256)
+gram_cross_kernel(const double* __restrict__ Z1, int64_t n1, const double* __restrict__ Z2, int64_t n2, int Df,
+                  int64_t ldz1, int64_t ldz2, double* __restrict__ K, int64_t ldk, int base, double scale,
+                  const double* __restrict__ col_scale) {
+    extern __shared__ __align__(16) double sm[];
+    double* si = sm;
+    double* sj = sm + Df * TILE;
+    const int64_t i0 = (int64_t)blockIdx.y * TILE, j0 = (int64_t)blockIdx.x * TILE;
+    stage_features(si, Z1, ldz1, i0, n1, Df);
+    stage_features(sj, Z2, ldz2, j0, n2, Df);
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+    tile_distances(si, sj, Df, ty, tx, acc);
+    double cs[4] = {1.0, 1.0, 1.0, 1.0};
+    if (col_scale) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t col = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+            cs[c] = col < n2 ? col_scale[col] : 0.0;
+        }
+    }
+    const bool full_cols = (j0 + TILE <= n2) && ((ldk & 1) == 0);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = i0 + ty + 16 * r;
+        if (row >= n1) continue;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int64_t col = j0 + 2 * tx + 32 * c;
+            const double v0 = base_eval(base, scale, acc[r][2 * c]) * cs[2 * c];
+            const double v1 = base_eval(base, scale, acc[r][2 * c + 1]) * cs[2 * c + 1];
+            double* p = K + row * ldk + col;
+            if (full_cols) {
+                *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
+            } else {
+                if (col < n2) p[0] = v0;
+                if (col + 1 < n2) p[1] = v1;
+            }
+        }
+    }
+}
+
+// B_ij = a*delta_ij + s_i (K_ij + jitter*delta_ij) s_j for j <= i (s == nullptr -> s = 1).
+__global__ void __launch_bounds__(256)
+sym_transform_kernel(const double* __restrict__ K, int64_t n, int64_t ldk, const double* __restrict__ s, double a,
+                     double jitter, double* __restrict__ B, int64_t ldb) {
+    int ti, tj;
+    tri_tile(blockIdx.x, ti, tj);
+    const int64_t i0 = (int64_t)ti * TILE, j0 = (int64_t)tj * TILE;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double sj[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int64_t col = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+        sj[c] = (s && col < n) ? s[col] : 1.0;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = i0 + ty + 16 * r;
+        if (row >= n) continue;
+        const double si = s ? s[row] : 1.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t col = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+            if (col > row) continue;
+            double v = K[row * ldk + col];
+            if (col == row) v = a + si * (v + jitter) * sj[c];
+            else v = si * v * sj[c];
+            B[row * ldb + col] = v;
+        }
+    }
+}
+
+inline int64_t tri_tiles(int64_t n) {
+    const int64_t T = ceil_div<int64_t>(n, TILE);
+    return T * (T + 1) / 2;
+}
+
+constexpr int GRAM_SMEM_SYM_MAX = (2 * MAX_DF * TILE + TILE * (TILE + 1)) * 8;
+constexpr int GRAM_SMEM_CROSS_MAX = (2 * MAX_DF * TILE) * 8;
+inline int gram_smem_sym(int Df) { return (2 * Df * TILE + TILE * (TILE + 1)) * 8; }
+inline int gram_smem_cross(int Df) { return (2 * Df * TILE) * 8; }
+
+}  // namespace
+
+int feature_dim(const pb_kernel_spec& spec, int D) { return spec.periodic ? 2 * D : D; }
+
+int check_spec(const pb_kernel_spec& spec) {
+    PB_CHECK(spec.base == PB_BASE_EQ || spec.base == PB_BASE_EXP, PB_ERR_UNSUPPORTED, "kernel base %d unsupported",
+             spec.base);
+    PB_CHECK(spec.stretch_in > 0 && spec.stretch_out > 0, PB_ERR_INVALID, "kernel stretch must be positive");
+    PB_CHECK(!spec.periodic || spec.period > 0, PB_ERR_INVALID, "kernel period must be positive");
+    return PB_OK;
+}
+
+int features(cudaStream_t stream, const pb_kernel_spec& spec, const double* X, int64_t n, int D, int64_t ldx,
+             double* Z, int64_t ldz) {
+    PB_TRY(check_spec(spec));
+    PB_CHECK(D >= 1 && feature_dim(spec, D) <= MAX_DF, PB_ERR_UNSUPPORTED, "feature dimension %d exceeds %d",
+             feature_dim(spec, D), MAX_DF);
+    if (n == 0) return PB_OK;
+    const int64_t want = ceil_div<int64_t>(n * D, 256);
+    const int64_t cap = (int64_t)num_sms() * 8;
+    features_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(X, n, D, ldx, Z, ldz, spec.periodic,
+                                                                             spec.stretch_in, spec.period,
+                                                                             spec.stretch_out);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+             double* K, int64_t ldk, const double* diag_vec, double diag_scalar) {
+    PB_TRY(check_spec(spec));
+    PB_CHECK(Df >= 1 && Df <= MAX_DF, PB_ERR_UNSUPPORTED, "feature dimension %d exceeds %d", Df, MAX_DF);
+    if (n == 0) return PB_OK;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(gram_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_SYM_MAX));
+        configured = true;
+    }
+    gram_sym_kernel<<<(unsigned)tri_tiles(n), 256, gram_smem_sym(Df), stream>>>(Z, n, Df, ldz, K, ldk, spec.base,
+                                                                           spec.scale, diag_vec, diag_scalar);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
+               int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale) {
+    PB_TRY(check_spec(spec));
+    PB_CHECK(Df >= 1 && Df <= MAX_DF, PB_ERR_UNSUPPORTED, "feature dimension %d exceeds %d", Df, MAX_DF);
+    if (n1 == 0 || n2 == 0) return PB_OK;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(gram_cross_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_CROSS_MAX));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div<int64_t>(n2, TILE), (unsigned)ceil_div<int64_t>(n1, TILE));
+    PB_CHECK(grid.y < 65536, PB_ERR_INVALID, "gram_cross: too many row tiles (chunk the rows)");
+    gram_cross_kernel<<<grid, 256, gram_smem_cross(Df), stream>>>(Z1, n1, Z2, n2, Df, ldz1, ldz2, K, ldk, spec.base,
+                                                             spec.scale, col_scale);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, const double* s, double a,
+                  double jitter, double* B, int64_t ldb) {
+    if (n == 0) return PB_OK;
+    sym_transform_kernel<<<(unsigned)tri_tiles(n), 256, 0, stream>>>(K, n, ldk, s, a, jitter, B, ldb);
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+}  // namespace pb
+
+extern "C" int pb_feature_dim(const pb_kernel_spec* spec, int D) { return pb::feature_dim(*spec, D); }
+
+extern "C" int pb_features(pb_stream_t stream, const pb_kernel_spec* spec, const double* X, int64_t n, int D,
+                           int64_t ldx, double* Z, int64_t ldz) {
+    return pb::features(reinterpret_cast<cudaStream_t>(stream), *spec, X, n, D, ldx, Z, ldz);
+}
+
+extern "C" int pb_gram_sym(pb_stream_t stream, const pb_kernel_spec* spec, const double* Z, int64_t n, int Df,
+                           int64_t ldz, double* K, int64_t ldk, const double* diag_vec, double diag_scalar) {
+    return pb::gram_sym(reinterpret_cast<cudaStream_t>(stream), *spec, Z, n, Df, ldz, K, ldk, diag_vec, diag_scalar);
+}
+
+extern "C" int pb_gram_cross(pb_stream_t stream, const pb_kernel_spec* spec, const double* Z1, int64_t n1,
+                             const double* Z2, int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K,
+                             int64_t ldk) {
+    return pb::gram_cross(reinterpret_cast<cudaStream_t>(stream), *spec, Z1, n1, Z2, n2, Df, ldz1, ldz2, K, ldk,
+                          nullptr);
+}
+
+extern "C" int pb_scale_sym_plus_identity(pb_stream_t stream, const double* K, int64_t n, int64_t ldk,
+                                          const double* s, double jitter, double* B, int64_t ldb) {
+    return pb::sym_transform(reinterpret_cast<cudaStream_t>(stream), K, n, ldk, s, 1.0, jitter, B, ldb);
+}
+
+extern "C" int pb_copy_lower_add_diag(pb_stream_t stream, const double* K, int64_t n, int64_t ldk,
+                                      double diag_scalar, double* A, int64_t lda) {
+    return pb::sym_transform(reinterpret_cast<cudaStream_t>(stream), K, n, ldk, nullptr, diag_scalar, 0.0, A, lda);
+}

@@ -1,0 +1,146 @@
+// Device functions of the per-datum likelihoods, shared by likelihood.cu and the fused
+// Newton-step kernels in fit.cu.  Reference: probit/utilities.py (line cites inline).
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+namespace lik {
+
+constexpr double OVER_SQRT_2PI = 0.3989422804014327;    // utilities.py:10
+constexpr double LOG_OVER_SQRT_2PI = -0.9189385332046727; // utilities.py:11
+constexpr double SQRT2 = 1.4142135623730951;             // utilities.py:12
+
+__device__ __forceinline__ double ndtr(double z) { return 0.5 * (1.0 + erf(z / SQRT2)); }   // utilities.py:18-19
+__device__ __forceinline__ double norm_z_pdf(double z) { return OVER_SQRT_2PI * exp(-0.5 * z * z); }  // :22-23
+__device__ __forceinline__ double norm_cdf(double x) {   // utilities.py:31-34
+    if (isinf(x)) return x > 0 ? 1.0 : 0.0;
+    return ndtr(x);
+}
+__device__ __forceinline__ double series_h(double z) {   // utilities.py:37-44
+    const double q = 1.0 / (z * z);
+    return -q + 2.5 * q * q - (37.0 / 3.0) * q * q * q;
+}
+__device__ __forceinline__ double z_far_tails(double z) {   // utilities.py:83-85
+    return OVER_SQRT_2PI / z * exp(-0.5 * z * z + series_h(z));
+}
+__device__ __forceinline__ double z_tails(double z1, double z2) { return z_far_tails(z1) - z_far_tails(z2); }  // :73-80
+
+struct Out { double ll, g, h, d3; };
+
+// utilities.py:56-57 and its first three derivatives in f
+__device__ __forceinline__ Out ordinal_autodiff(double f, double b1, double b2, double sigma, double eps) {
+    const bool fin1 = b1 != -INFINITY, fin2 = b2 != INFINITY;
+    const double z1 = fin1 ? (b1 - f) / sigma : 0.0;    // utilities.py:217,219-221
+    const double z2 = fin2 ? (b2 - f) / sigma : 0.0;    // utilities.py:218,222-224
+    const double cdf1 = fin1 ? norm_cdf(z1) : 0.0;
+    const double cdf2 = fin2 ? norm_cdf(z2) : 1.0;
+    const double p1 = fin1 ? norm_z_pdf(z1) : 0.0;
+    const double p2 = fin2 ? norm_z_pdf(z2) : 0.0;
+    const double u = (cdf2 - cdf1) + eps;               // utilities.py:225, :57
+    Out o;
+    o.ll = log(u);
+    o.g = (p1 - p2) / (sigma * u);
+    o.h = (z1 * p1 - z2 * p2) / (sigma * sigma * u) - o.g * o.g;
+    o.d3 = ((z1 * z1 - 1.0) * p1 - (z2 * z2 - 1.0) * p2) / (sigma * sigma * sigma * u) - 3.0 * o.g * o.h -
+           o.g * o.g * o.g;
+    return o;
+}
+
+// utilities.py:88-148
+__device__ __forceinline__ void safe_Z(double f, double bt, double btp1, double sigma, double ub, double ub2,
+                                       double ub3, double& Z, double& z1s, double& z2s) {
+    const double SAFE = 1.0;
+    const double _b = (btp1 == INFINITY) ? 0.0 : btp1;
+    const double _a = (bt == -INFINITY) ? 0.0 : bt;
+    z2s = (btp1 == INFINITY) ? INFINITY : (_b - f) / sigma;
+    z1s = (bt == -INFINITY) ? -INFINITY : (_a - f) / sigma;
+    Z = norm_cdf(z2s) - norm_cdf(z1s);
+    double _z1s = (ub < z1s && z1s <= ub2) ? z1s : SAFE;
+    const double __z2s = (ub < z1s) ? z2s : SAFE;
+    double _z2s = (-ub2 <= z2s && z2s < -ub) ? z2s : SAFE;
+    const double __z1s = (-ub > z2s) ? z1s : SAFE;
+    Z = (z1s > ub) ? z_tails(_z1s, __z2s) : Z;
+    Z = (z2s < -ub) ? z_tails(__z1s, _z2s) : Z;
+    _z1s = (ub2 < fabs(z1s) && fabs(z1s) < ub3) ? z1s : SAFE;
+    _z2s = (ub2 < fabs(z2s) && fabs(z2s) < ub3) ? z2s : SAFE;
+    Z = (z1s > ub2) ? z_far_tails(_z1s) : Z;
+    Z = (z2s < -ub2) ? z_far_tails(-_z2s) : Z;
+    Z = (z1s >= ub3) ? SAFE : Z;
+    Z = (z2s <= -ub3) ? SAFE : Z;
+}
+
+// utilities.py:151-192; ll and d3 stay the autodiff expressions (the reference defines no safe ll)
+__device__ __forceinline__ Out ordinal_safe(double f, double b1, double b2, double sigma, double eps, double ub,
+                                            double ub2, double ub3) {
+    Out o = ordinal_autodiff(f, b1, b2, sigma, eps);
+    double Z, z1s, z2s;
+    safe_Z(f, b1, b2, sigma, ub, ub2, ub3, Z, z1s, z2s);
+    const double p1 = norm_z_pdf(z1s), p2 = norm_z_pdf(z2s);
+    double E = (p1 - p2) / Z;
+    E = (z1s > ub3) ? z1s : E;
+    E = (z2s < -ub3) ? z2s : E;
+    const double w = E / sigma;
+    const double _z1 = isinf(z1s) ? 0.0 : z1s, _z2 = isinf(z2s) ? 0.0 : z2s;
+    double V = -(w * w) + (_z1 * p1 - _z2 * p2) / Z / (sigma * sigma);
+    V = (z1s > ub3) ? -1.0 / (sigma * sigma) : V;
+    V = (z2s < -ub3) ? -1.0 / (sigma * sigma) : V;
+    o.g = w;
+    o.h = V;
+    return o;
+}
+
+__device__ __forceinline__ Out gaussian(double f, double y, double sigma) {
+    const double z = (f - y) / sigma;                     // utilities.py:68-70
+    Out o;
+    o.ll = LOG_OVER_SQRT_2PI - z * z / 2.0 - log(sigma);  // utilities.py:64-65,70
+    o.g = (y - f) / (sigma * sigma);
+    o.h = -1.0 / (sigma * sigma);
+    o.d3 = 0.0;
+    return o;
+}
+
+
+constexpr int MAX_CUT = 256;
+
+struct Params {
+    int kind;
+    int J;
+    double sigma, eps, ub, ub2, ub3;
+};
+
+inline int make_params(const pb_likelihood_spec& l, Params& p) {
+    p.kind = l.kind; p.J = l.J; p.sigma = l.sigma; p.eps = l.eps;
+    p.ub = p.ub2 = p.ub3 = 0.0;
+    PB_CHECK(l.sigma > 0, PB_ERR_INVALID, "likelihood: sigma must be positive");
+    if (l.kind == PB_LIK_GAUSSIAN) return PB_OK;
+    PB_CHECK(l.kind == PB_LIK_ORDINAL_PROBIT || l.kind == PB_LIK_ORDINAL_PROBIT_SAFE, PB_ERR_UNSUPPORTED,
+             "likelihood: unknown kind %d", l.kind);
+    PB_CHECK(l.J >= 1 && l.J <= MAX_CUT, PB_ERR_INVALID, "likelihood: J must be in [1, %d]", MAX_CUT);
+    PB_CHECK(l.cutpoints != nullptr, PB_ERR_INVALID, "likelihood: cutpoints missing");
+    if (l.kind == PB_LIK_ORDINAL_PROBIT_SAFE) {
+        if (l.safe_single_precision) { p.ub = 1.3; p.ub2 = 1.8; p.ub3 = 2.3; }   // utilities.py:15
+        else { p.ub = 2.3; p.ub2 = 3.6; p.ub3 = 4.8; }
+    }
+    return PB_OK;
+}
+
+// Evaluate datum d: `sc` = cutpoints staged in shared memory (ordinal kinds).
+__device__ __forceinline__ Out eval(const Params& p, double f, const void* __restrict__ yv, int64_t d,
+                                    const double* sc) {
+    if (p.kind == PB_LIK_GAUSSIAN) return gaussian(f, reinterpret_cast<const double*>(yv)[d], p.sigma);
+    long long yi = reinterpret_cast<const long long*>(yv)[d];
+    yi = yi < 0 ? 0 : (yi >= p.J ? p.J - 1 : yi);     // JAX clamps out-of-range gather indices
+    const double b1 = sc[yi], b2 = sc[yi + 1];
+    return p.kind == PB_LIK_ORDINAL_PROBIT ? ordinal_autodiff(f, b1, b2, p.sigma, p.eps)
+                                           : ordinal_safe(f, b1, b2, p.sigma, p.eps, p.ub, p.ub2, p.ub3);
+}
+
+__device__ __forceinline__ void stage_cutpoints(const Params& p, const double* __restrict__ cut, double* sc) {
+    if (p.kind != PB_LIK_GAUSSIAN) {
+        for (int i = threadIdx.x; i <= p.J; i += blockDim.x) sc[i] = cut[i];
+    }
+    __syncthreads();
+}
+
+}  // namespace lik
+}  // namespace pb

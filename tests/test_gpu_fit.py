@@ -1,0 +1,88 @@
+"""GPU parity tests of the fit / predict drivers against the oracle (same seeded inputs)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from helpers import make_prior, ordinal_problem, regression_problem, relerr  # noqa: E402
+from oracle import approximators as OA, kernels as OK, utilities as OU  # noqa: E402
+
+TOL = 1e-8   # BASELINE.json north_star: 1e-8 relative in float64
+
+
+def _pair(X, y, family, gaussian=False, cls="LaplaceGP", **okw):
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    o = getattr(OA, cls)((X, y), make_prior(OK, family),
+                         OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood, **okw)
+    p = getattr(PA, cls)((X, y), make_prior(PK, family),
+                         PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood)
+    return o, p
+
+
+@pytest.mark.parametrize("N,D,J,family", [(30, 1, 3, "eq"), (250, 4, 5, "matern12"), (1000, 4, 5, "matern12"),
+                                          (999, 2, 3, "eq")])
+def test_laplace_ordinal_matches_oracle(N, D, J, family):
+    X, y, params, _ = ordinal_problem(N + J, N, D, J, family)
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)          # literal: dense Jacobian + LU
+    w, prec = p.approximate_posterior(params)
+    assert p.last_result.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL
+    assert relerr(prec.cpu().numpy(), p_ref) < TOL
+    Xs = np.random.default_rng(0).uniform(-0.5, 1.5, size=(257, D))
+    m_ref, v_ref = o.predict(Xs, params, w_ref, p_ref)
+    m, v = p.predict(Xs, params, w, prec)
+    assert relerr(m.cpu().numpy(), m_ref) < TOL
+    assert relerr(v.cpu().numpy(), v_ref) < TOL
+    obj_ref = o.objective()(params)
+    obj = p.objective()(params)
+    assert abs(obj - obj_ref) < TOL * abs(obj_ref)
+
+
+def test_laplace_gaussian_is_exact_gp_regression():
+    X, y, params, family = regression_problem(0, 20)       # examples/regression.py config
+    o, p = _pair(X, y, family, gaussian=True)
+    w, prec = p.approximate_posterior(params)
+    K = make_prior(OK, family)(params[0])(X)
+    s2 = params[1][0] ** 2
+    w_closed = np.linalg.solve(K + s2 * np.eye(20), y)
+    assert relerr(w.cpu().numpy(), w_closed) < 1e-10
+    assert np.allclose(prec.cpu().numpy(), 1 / s2)
+    assert p.last_result.iterations == 2
+    nlml = 0.5 * y @ w_closed + 0.5 * np.linalg.slogdet(K + s2 * np.eye(20))[1] + 10 * np.log(2 * np.pi)
+    assert abs(p.objective()(params) - nlml) < 1e-9 * abs(nlml)
+    Xs = np.linspace(-0.5, 1.5, 1000)[:, None]
+    m, v = p.predict(Xs, params, w, prec)
+    m_ref, v_ref = o.predict(Xs, params, w_closed, np.full(20, 1 / s2))
+    assert relerr(m.cpu().numpy(), m_ref) < TOL
+    assert np.abs(v.cpu().numpy() - v_ref).max() < 1e-9
+
+
+@pytest.mark.parametrize("N,D,J", [(30, 1, 3), (500, 4, 5)])
+def test_vb_matches_oracle(N, D, J):
+    X, y, params, family = ordinal_problem(N, N, D, J, "eq")
+    o, p = _pair(X, y, family, cls="VBGP")
+    w_ref, p_ref = o.approximate_posterior(params)
+    w, prec = p.approximate_posterior(params)
+    assert p.last_result.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL
+    assert np.allclose(prec.cpu().numpy(), p_ref)
+    obj_ref = o.objective()(params)
+    assert abs(p.objective()(params) - obj_ref) < TOL * abs(obj_ref)
+    Xs = np.random.default_rng(1).uniform(-0.5, 1.5, size=(100, D))
+    m_ref, v_ref = o.predict(Xs, params, w_ref, p_ref)
+    m, v = p.predict(Xs, params, w, prec)
+    assert relerr(m.cpu().numpy(), m_ref) < TOL
+    assert relerr(v.cpu().numpy(), v_ref) < TOL
+
+
+def test_construct_and_precision_helpers():
+    X, y, params, family = ordinal_problem(7, 120, 2, 3, "eq")
+    o, p = _pair(X, y, family)
+    w = np.random.default_rng(0).normal(size=120) * 0.1
+    f_ref = o.construct()(params, w)
+    f = p.construct()(params, w)
+    assert relerr(f.cpu().numpy(), f_ref) < 1e-12
+    pr, m = p.precision(w, params)
+    pr_ref, m_ref = o.precision(w, params)
+    assert relerr(pr.cpu().numpy(), pr_ref) < 1e-11 and relerr(m.cpu().numpy(), m_ref) < 1e-13

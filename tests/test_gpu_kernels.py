@@ -1,0 +1,184 @@
+"""GPU parity tests of the individual CUDA kernels, all called through the C ABI (ctypes)."""
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+pytestmark = pytest.mark.gpu
+
+from helpers import relerr  # noqa: E402
+from oracle import kernels as OK, utilities as OU  # noqa: E402
+
+
+def _torch():
+    import torch
+    return torch
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (256, 128, 64), (300, 200, 100), (64, 64, 64), (1, 1, 1),
+                                   (1000, 40, 40), (513, 257, 129), (2048, 1024, 512)])
+def test_gemm_nt_matches_fp64_matmul(M, N, K):
+    torch = _torch()
+    from probit_b200 import linalg
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    A = linalg.empty_matrix(M, K); A.copy_(torch.randn(M, K, dtype=torch.float64, device="cuda", generator=g))
+    B = linalg.empty_matrix(N, K); B.copy_(torch.randn(N, K, dtype=torch.float64, device="cuda", generator=g))
+    C0 = linalg.empty_matrix(M, N); C0.copy_(torch.randn(M, N, dtype=torch.float64, device="cuda", generator=g))
+    ref = 0.5 * (A @ B.T) - 2.0 * C0
+    out = linalg.gemm_nt(A, B, C0.clone() if False else C0, alpha=0.5, beta=-2.0)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item() / max(ref.abs().max().item(), 1e-300)
+    assert err < 1e-13, err
+
+
+def test_gemm_nt_lower_only_leaves_upper_untouched():
+    torch = _torch()
+    from probit_b200 import linalg
+    n, k = 700, 96
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = linalg.empty_matrix(n, k); A.copy_(torch.randn(n, k, dtype=torch.float64, device="cuda", generator=g))
+    C = linalg.empty_matrix(n, n); C.fill_(7.0)
+    linalg.gemm_nt(A, A, C, alpha=-1.0, beta=1.0, lower_only=True)
+    ref = 7.0 - A @ A.T
+    assert torch.allclose(torch.tril(C), torch.tril(ref), rtol=1e-13, atol=1e-12)
+    assert torch.all(torch.triu(C, 1) == torch.triu(torch.full_like(C, 7.0), 1))
+
+
+@pytest.mark.parametrize("n", [1, 5, 31, 32, 33, 64, 65, 100, 128, 200, 513, 1000, 2500])
+def test_potrf_matches_lapack(n):
+    torch = _torch()
+    from probit_b200 import linalg
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n, n + 5))
+    A = G @ G.T + n * 0.01 * np.eye(n)
+    Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
+    Ad_upper_before = torch.triu(Ad, 1).clone()
+    fac = linalg.potrf_(Ad)
+    L = np.tril(Ad.cpu().numpy())
+    Lref = np.linalg.cholesky(A)
+    assert relerr(L, Lref) < 1e-12
+    assert torch.equal(torch.triu(Ad, 1), Ad_upper_before)       # strict upper never written
+    # solves through the leaf inverses
+    b = rng.standard_normal(n)
+    x = linalg.cholesky_solve(fac, torch.as_tensor(b, device="cuda")).cpu().numpy()
+    assert relerr(x, np.linalg.solve(A, b)) < 1e-9
+    ld = linalg.logdet_chol(fac).item()
+    assert abs(ld - np.sum(np.log(np.diag(Lref)))) < 1e-10 * max(1.0, abs(ld))
+    # many-RHS right solve X L^-T
+    Xr = rng.standard_normal((37, n))
+    Xd = linalg.empty_matrix(37, n); Xd.copy_(torch.as_tensor(Xr, device="cuda"))
+    linalg.trsm_right_lt_(fac, Xd)
+    ref = sla.solve_triangular(Lref, Xr.T, lower=True).T
+    assert relerr(Xd.cpu().numpy(), ref) < 1e-10
+
+
+def test_potrf_reports_first_bad_pivot():
+    torch = _torch()
+    from probit_b200 import linalg, _lib
+    n = 300
+    A = np.eye(n); A[150, 150] = -1.0
+    Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
+    fac = linalg.potrf_(Ad, check=False)
+    assert int(fac.info.item()) == 151
+    Ad.copy_(torch.as_tensor(A, device="cuda"))
+    with pytest.raises(_lib.NumericError):
+        linalg.potrf_(Ad)
+
+
+@pytest.mark.parametrize("family,D", [("eq", 1), ("eq", 8), ("matern12", 4), ("eq_periodic", 1), ("eq_periodic", 3)])
+@pytest.mark.parametrize("n", [1, 63, 64, 130, 257])
+def test_gram_matches_oracle(family, D, n):
+    torch = _torch()
+    from probit_b200 import kernels as PK
+    from helpers import make_prior
+    rng = np.random.default_rng(n + D)
+    X = rng.uniform(0, 1, size=(n, D))
+    Y = rng.uniform(-0.5, 1.5, size=(45, D))
+    th = 0.7 if family in ("eq", "matern12") else (0.7, 1.3)
+    ko, kp = make_prior(OK, family)(th), make_prior(PK, family)(th)
+    Kref = ko(X)
+    K = kp(X).cpu().numpy()
+    assert np.abs(K - Kref).max() < 1e-14 * max(1.0, np.abs(Kref).max())
+    assert np.array_equal(K, K.T)                                  # mirror store is exact
+    Kc = kp(X, Y).cpu().numpy()
+    assert np.abs(Kc - ko(X, Y)).max() < 1e-14 * max(1.0, np.abs(Kref).max())
+
+
+def test_gram_diag_add():
+    torch = _torch()
+    from probit_b200 import kernels as PK, linalg
+    rng = np.random.default_rng(0)
+    X = rng.uniform(0, 1, size=(150, 2))
+    dv = rng.uniform(0.1, 1, size=150)
+    k = 2.0 * PK.EQ().stretch(0.5)
+    K = linalg.gram(k.lower(), X, diag_add=1e-3, diag_vec=dv).cpu().numpy()
+    ref = (2.0 * OK.EQ().stretch(0.5))(X) + 1e-3 * np.eye(150) + np.diag(dv)
+    assert np.abs(K - ref).max() < 1e-14
+
+
+def _ordinal_inputs(n, J, seed):
+    rng = np.random.default_rng(seed)
+    cut = np.concatenate([[-np.inf], np.sort(rng.normal(0, 1, J - 1)), [np.inf]])
+    y = rng.integers(0, J, size=n)
+    f = rng.normal(0, 2.5, size=n)
+    return f, y, (0.63, cut)
+
+
+@pytest.mark.parametrize("J", [2, 3, 5, 11])
+def test_ordinal_likelihood_matches_oracle(J):
+    from probit_b200 import utilities as PU, _lib
+    f, y, lp = _ordinal_inputs(4099, J, J)
+    out = PU.evaluate_likelihood(_lib.PB_LIK_ORDINAL_PROBIT, f, y, lp, ("ll", "g", "h", "d3"))
+    ref = {"ll": OU.log_probit_likelihood(f, y, lp), "g": OU.grad_log_probit_likelihood_autodiff(f, y, lp),
+           "h": OU.hessian_log_probit_likelihood_autodiff(f, y, lp),
+           "d3": OU.third_log_probit_likelihood_autodiff(f, y, lp)}
+    # CUDA erf and SciPy erf differ by ~1 ulp, i.e. ~2e-16 ABSOLUTE on Z; every output divides by
+    # u = Z + eps (up to the third power for d3), so the admissible error is a few ulp / u relative to
+    # the output magnitude.  Where Z is O(1) this is rounding level.
+    u = OU.probit_likelihood(f, y, lp) + 1e-10
+    amp = {"ll": 8.0, "g": 16.0, "h": 64.0, "d3": 256.0}
+    for k in ref:
+        got = out[k].cpu().numpy()
+        assert np.all(np.isfinite(got))
+        bound = amp[k] * 2.3e-16 / u * (1.0 + np.abs(ref[k])) + 1e-13 * (1.0 + np.abs(ref[k]))
+        assert np.all(np.abs(got - ref[k]) <= bound), (k, np.max(np.abs(got - ref[k]) / bound))
+
+
+def test_gaussian_and_safe_likelihood_match_oracle():
+    from probit_b200 import utilities as PU, _lib
+    rng = np.random.default_rng(3)
+    f, yv = rng.normal(size=1000), rng.normal(size=1000)
+    out = PU.evaluate_likelihood(_lib.PB_LIK_GAUSSIAN, f, yv, (0.3,), ("ll", "g", "h", "d3"))
+    assert np.allclose(out["ll"].cpu().numpy(), OU.log_gaussian_likelihood(f, yv, (0.3,)), rtol=1e-14, atol=1e-14)
+    assert np.allclose(out["g"].cpu().numpy(), OU.grad_log_gaussian_likelihood(f, yv, (0.3,)), rtol=1e-14)
+    assert np.allclose(out["h"].cpu().numpy(), OU.hessian_log_gaussian_likelihood(f, yv, (0.3,)), rtol=1e-14)
+    assert np.all(out["d3"].cpu().numpy() == 0)
+    for single in (True, False):
+        f, y, lp = _ordinal_inputs(5000, 5, 9)
+        g = PU.grad_log_probit_likelihood(f, y, lp, single).cpu().numpy()
+        h = PU.hessian_log_probit_likelihood(f, y, lp, single).cpu().numpy()
+        gr, hr = OU.grad_log_probit_likelihood(f, y, lp, single), OU.hessian_log_probit_likelihood(f, y, lp, single)
+        assert np.max(np.abs(g - gr) / (1 + np.abs(gr))) < 1e-10
+        assert np.max(np.abs(h - hr) / (1 + np.abs(hr))) < 1e-10
+
+
+def test_predictive_distributions_match_oracle():
+    from probit_b200 import utilities as PU
+    rng = np.random.default_rng(5)
+    m, v = rng.normal(size=3001), rng.uniform(0.01, 2, size=3001)
+    cut = np.array([-np.inf, -0.5, 0.1, 0.9, np.inf])
+    P = PU.probit_predictive_distributions((0.6, cut), m, v).cpu().numpy()
+    ref = OU.probit_predictive_distributions((0.6, cut), m, v)
+    assert np.abs(P - ref).max() < 1e-14
+    assert np.abs(P.sum(1) - 1).max() < 1e-14
+
+
+def test_symv_and_trsv_large_ragged():
+    torch = _torch()
+    from probit_b200 import linalg
+    n = 1237
+    rng = np.random.default_rng(2)
+    A = rng.standard_normal((n, n)); A = A + A.T
+    Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
+    x = rng.standard_normal(n)
+    y = linalg.symv(Ad, torch.as_tensor(x, device="cuda")).cpu().numpy()
+    assert relerr(y, A @ x) < 1e-13

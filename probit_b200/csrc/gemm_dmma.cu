@@ -6,10 +6,10 @@
 // (measured peak 37.0 TFLOP/s on B200, profiles/r01_fp64_peaks.json).
 //
 // Design
-//  * CTA tile 128x128, K step 16 doubles (= one 128-byte TMA swizzle span).
-//  * One producer warp: a single elected lane drives a STAGES-deep ring of TMA box loads
-//    (cp.async.bulk.tensor.2d, SWIZZLE_128B) signalled through mbarriers (full/empty pairs).
-//  * Eight consumer warps (2 x 4), warp tile 64x32 -> 32 m8n8k4 accumulators (64 doubles/lane).
+//  * CTA tile 128x64 (two CTAs per SM), K step 16 doubles (= one 128-byte TMA swizzle span).
+//  * Thread 0 drives a STAGES-deep ring of TMA box loads (cp.async.bulk.tensor.2d, SWIZZLE_128B)
+//    signalled through mbarriers (full/empty pairs), keeping STAGES-1 loads in flight.
+//  * Eight warps (4 x 2), warp tile 32x32 -> 16 m8n8k4 accumulators (32 doubles/lane).
 //  * Bank-conflict-free fragment loads under the 128B swizzle: the 8 rows of an m8 fragment are
 //    taken in the order perm(g) = 2*(g&3) + (g>>2), so the 16 lanes of each LDS.64 phase touch
 //    16 distinct 8-byte bank pairs.  The permutation is undone when C is addressed.
@@ -17,20 +17,37 @@
 //    epilogue masks stores.
 //  * `lower_only` enumerates only tiles with tile_n <= tile_m in L2-friendly column strips.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pb {
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 6;
-constexpr int CONSUMER_WARPS = 8;
-constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
-constexpr int A_STAGE_BYTES = BM * BK * 8;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 8;  // 16 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+constexpr int BK = 16;
 constexpr int STRIP_W = 12;  // tiles per column strip in the lower-only rasterisation
+
+// Tile configuration: CTA tile BM x BN, WM x WN warps.
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MIN_CTAS_>
+struct Cfg {
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MIN_CTAS = MIN_CTAS_;
+    static constexpr int CONSUMER_WARPS = WM * WN;
+    static constexpr int THREADS = CONSUMER_WARPS * 32;
+    static constexpr int WARP_M = BM / WM, WARP_N = BN / WN;     // warp tile
+    static constexpr int MI = WARP_M / 8, NJ = WARP_N / 8;       // m8n8 accumulator tiles per warp
+    static constexpr int A_STAGE_BYTES = BM * BK * 8;
+    static constexpr int B_STAGE_BYTES = BN * BK * 8;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 2 * STAGES * 8;
+};
+// Measured on B200 (SYRK 16384 x K, TFLOP/s of the 37.0 DMMA peak), profiles/r01_gemm_configs.md:
+//   128x128, 8 warps of 64x32, 1 CTA/SM : K=512 32.3   K=8192 34.0   (prologue/epilogue exposed)
+//   128x64,  4 warps of 64x32, 2 CTA/SM : K=512 32.6   (one warp per sub-partition cannot saturate DMMA)
+//   128x64,  4 warps of 64x32, 3 CTA/SM : K=512 34.4
+//   128x64,  8 warps of 32x32, 2 CTA/SM : K=512 34.7   K=1024 35.4   K=8192 35.1   <- CfgMain
+// Two co-resident CTAs hide each other's prologue (C prefetch, pipeline fill) and epilogue, and the
+// other CTA still has two warps per sub-partition, which is what it takes to keep the DMMA pipe full.
+using CfgMain = Cfg<128, 64, 4, 2, 4, 2>;
+using CfgSmall = Cfg<64, 64, 2, 2, 4, 3>;    // 4 warps of 32x32, 3 CTAs/SM: panel / leaf-sized problems
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -105,22 +122,37 @@ __device__ __forceinline__ void lower_tile(int bid, int T, int& tm, int& tn) {
     }
 }
 
-__global__ void __launch_bounds__(THREADS, 1)
+// Same for BM = 2*BN tiles (row-major over tile rows): tile row tm needs column tiles 0 .. 2*tm+1.
+__device__ __forceinline__ void lower_tile_2to1(int bid, int& tm, int& tn) {
+    int r = (int)((sqrtf(4.0f * bid + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) <= bid) ++r;
+    while (r * (r + 1) > bid) --r;
+    tm = r;
+    tn = bid - r * (r + 1);
+}
+
+template <class CF>
+__global__ void __launch_bounds__(CF::THREADS, CF::MIN_CTAS)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
                int lower_only, int tiles_n) {
+    constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES, CONSUMER_WARPS = CF::CONSUMER_WARPS;
+    constexpr int A_STAGE_BYTES = CF::A_STAGE_BYTES, STAGE_BYTES = CF::STAGE_BYTES;
+    constexpr int MI = CF::MI, NJ = CF::NJ, WARP_M = CF::WARP_M, WARP_N = CF::WARP_N;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
 
     int tile_m, tile_n;
     if (lower_only) {
-        lower_tile(blockIdx.x, tiles_n, tile_m, tile_n);
+        if (CF::BM == CF::BN) lower_tile(blockIdx.x, tiles_n, tile_m, tile_n);
+        else lower_tile_2to1(blockIdx.x, tile_m, tile_n);
     } else {
         tile_m = blockIdx.x / tiles_n;
         tile_n = blockIdx.x % tiles_n;
     }
     const int m0 = tile_m * BM, n0 = tile_n * BN;
+    if (m0 >= M || n0 >= N) return;               // whole CTA leaves together (2:1 lower rasterisation overshoot)
     const int kblocks = (K + BK - 1) / BK;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -134,85 +166,118 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     __syncthreads();
 
-    if (warp == CONSUMER_WARPS) {
-        // ===== TMA producer =====
-        if (lane == 0) {
-            for (int kb = 0; kb < kblocks; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t round = kb / STAGES;
-                if (kb >= STAGES) mbar_wait(bar_base + 8 * (STAGES + s), (round - 1) & 1);
-                const uint32_t full = bar_base + 8 * s;
-                mbar_expect_tx(full, STAGE_BYTES);
-                const uint32_t dstA = smem_base + s * STAGE_BYTES;
-                tma_load_2d(dstA, &mapA, kb * BK, m0, full);
-                tma_load_2d(dstA + A_STAGE_BYTES, &mapB, kb * BK, n0, full);
-            }
-        }
-        return;
+    // ===== TMA producer duty: thread 0 keeps STAGES-1 loads in flight from inside the consumer loop.
+    // (A dedicated 9th producer warp would put 3 warps on one SM sub-partition and cap every thread
+    // at 168 registers — the register file is 16K per sub-partition — which spills the 128-register
+    // accumulator tile; with 8 warps the cap is 255.)
+    auto issue_stage = [&](int kb) {
+        const int s = kb % STAGES;
+        const uint32_t full = bar_base + 8 * s;
+        mbar_expect_tx(full, STAGE_BYTES);
+        const uint32_t dstA = smem_base + s * STAGE_BYTES;
+        tma_load_2d(dstA, &mapA, kb * BK, m0, full);
+        tma_load_2d(dstA + A_STAGE_BYTES, &mapB, kb * BK, n0, full);
+    };
+    if (threadIdx.x == 0) {
+        const int pre = kblocks < STAGES - 1 ? kblocks : STAGES - 1;
+        for (int kb = 0; kb < pre; ++kb) issue_stage(kb);
     }
 
     // ===== consumers =====
-    const int wm = warp >> 2, wn = warp & 3;      // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp / CF::WN, wn = warp % CF::WN;
     const int g = lane >> 2, t = lane & 3;
     const int pg = perm8(g);
 
-    double acc[8][4][2];
+    // C is folded into the accumulators up front (acc = (beta/alpha) C): the loads overlap the TMA
+    // pipeline fill and the epilogue becomes store-only (a read-modify-write epilogue cost ~8 serial
+    // DRAM round trips per tile, 14% of a K=512 tile).
+    const int c0 = perm8(2 * t), c1 = perm8(2 * t + 1);
+    double acc[MI][NJ][2];
+    if (beta != 0.0) {
+        // All MI*NJ*2 loads are issued back to back (volatile asm keeps them ahead of the scaling, which
+        // depends on a value produced after the last load), so the tile costs one DRAM round trip
+        // instead of one per row group.  Masked elements read C[0] (always valid) and are zeroed.
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < MI; ++i) {
+            const int row = m0 + wm * WARP_M + 8 * i + pg;
+            const double* crow = C + (int64_t)row * ldc;
+            const int col_lim = row < M ? (lower_only ? min(N, row + 1) : N) : 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int j = 0; j < NJ; ++j) {
+                const int cb = n0 + wn * WARP_N + 8 * j;
+                const double* p0 = (cb + c0 < col_lim) ? crow + cb + c0 : C;
+                const double* p1 = (cb + c1 < col_lim) ? crow + cb + c1 : C;
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(acc[i][j][0]) : "l"(p0));
+                asm volatile("ld.global.f64 %0, [%1];" : "=d"(acc[i][j][1]) : "l"(p1));
+            }
+        }
+        double cs;
+        asm volatile("mov.f64 %0, %1;" : "=d"(cs) : "d"(beta / alpha));
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            const int row = m0 + wm * WARP_M + 8 * i + pg;
+            const int col_lim = row < M ? (lower_only ? min(N, row + 1) : N) : 0;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int cb = n0 + wn * WARP_N + 8 * j;
+                acc[i][j][0] = (cb + c0 < col_lim) ? cs * acc[i][j][0] : 0.0;
+                acc[i][j][1] = (cb + c1 < col_lim) ? cs * acc[i][j][1] : 0.0;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < MI; ++i)
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    }
 
     // byte offset inside a tile of (row = base + 8*i + pg, k = 4*ks + t) under SWIZZLE_128B
     uint32_t koff[4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) koff[ks] = ((((2 * ks) | (t >> 1)) ^ pg) << 4) | ((t & 1) << 3);
-    const uint32_t a_row = (wm * 64 + pg) * 128;
-    const uint32_t b_row = A_STAGE_BYTES + (wn * 32 + pg) * 128;
+    const uint32_t a_row = (wm * WARP_M + pg) * 128;
+    const uint32_t b_row = A_STAGE_BYTES + (wn * WARP_N + pg) * 128;
 
     for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % STAGES;
+        if (threadIdx.x == 0) {
+            const int nk = kb + STAGES - 1;               // refill the stage consumed in iteration kb-1
+            if (nk < kblocks) {
+                if (kb >= 1) mbar_wait(bar_base + 8 * (STAGES + (nk % STAGES)), ((kb - 1) / STAGES) & 1);
+                issue_stage(nk);
+            }
+        }
+        __syncwarp();
         mbar_wait(bar_base + 8 * s, (kb / STAGES) & 1);
         const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            double a[8], b[4];
+            double a[MI], b[NJ];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = lds64(st + a_row + i * 1024 + koff[ks]);
+            for (int i = 0; i < MI; ++i) a[i] = lds64(st + a_row + i * 1024 + koff[ks]);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = lds64(st + b_row + j * 1024 + koff[ks]);
+            for (int j = 0; j < NJ; ++j) b[j] = lds64(st + b_row + j * 1024 + koff[ks]);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
     }
 
-    // ===== epilogue: C = alpha * acc + beta * C (direct global access, permutation undone) =====
-    const int c0 = perm8(2 * t), c1 = perm8(2 * t + 1);
+    // ===== epilogue: C = alpha * acc (store-only; the row/column permutation is undone here) =====
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = m0 + wm * 64 + 8 * i + pg;
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * WARP_M + 8 * i + pg;
         if (row >= M) continue;
         double* crow = C + (int64_t)row * ldc;
         const int col_lim = lower_only ? min(N, row + 1) : N;
-        double old[4][2];
-        if (beta != 0.0) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int cb = n0 + wn * 32 + 8 * j;
-                old[j][0] = (cb + c0 < col_lim) ? crow[cb + c0] : 0.0;
-                old[j][1] = (cb + c1 < col_lim) ? crow[cb + c1] : 0.0;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int cb = n0 + wn * 32 + 8 * j;
-            double v0 = alpha * acc[i][j][0], v1 = alpha * acc[i][j][1];
-            if (beta != 0.0) { v0 += beta * old[j][0]; v1 += beta * old[j][1]; }
-            if (cb + c0 < col_lim) crow[cb + c0] = v0;
-            if (cb + c1 < col_lim) crow[cb + c1] = v1;
+        for (int j = 0; j < NJ; ++j) {
+            const int cb = n0 + wn * WARP_N + 8 * j;
+            if (cb + c0 < col_lim) crow[cb + c0] = alpha * acc[i][j][0];
+            if (cb + c1 < col_lim) crow[cb + c1] = alpha * acc[i][j][1];
         }
     }
 }
@@ -251,25 +316,25 @@ int make_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, i
     return PB_OK;
 }
 
-}  // namespace
-
-int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
-    if (M <= 0 || N <= 0) return PB_OK;
-    PB_CHECK(K > 0, PB_ERR_INVALID, "gemm_nt: K must be positive");
-    PB_CHECK(!lower_only || M == N, PB_ERR_INVALID, "gemm_nt: lower_only needs a square C");
-    PB_CHECK(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PB_ERR_INVALID, "gemm_nt: dimension too large");
+template <class CF>
+int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
     static bool configured = false;
     if (!configured) {
-        PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     CUtensorMap mapA, mapB;
-    PB_TRY(make_map(&mapA, A, M, K, lda, BM));
-    PB_TRY(make_map(&mapB, B, N, K, ldb, BN));
-    const int tm = (int)ceil_div<int64_t>(M, BM), tn = (int)ceil_div<int64_t>(N, BN);
+    PB_TRY(make_map(&mapA, A, M, K, lda, CF::BM));
+    PB_TRY(make_map(&mapB, B, N, K, ldb, CF::BN));
+    const int tm = (int)ceil_div<int64_t>(M, CF::BM), tn = (int)ceil_div<int64_t>(N, CF::BN);
     int64_t blocks;
-    if (lower_only) {
+    static_assert(CF::BM == CF::BN || CF::BM == 2 * CF::BN, "lower-only rasterisation supports 1:1 and 2:1 tiles");
+    if (lower_only && CF::BM != CF::BN) {
+        blocks = (int64_t)tm * (tm + 1);          // may include column tiles past N in the last row: they exit early
+    } else if (lower_only) {
         blocks = 0;
         for (int c0 = 0; c0 < tn; c0 += STRIP_W) {
             int w = tn - c0 < STRIP_W ? tn - c0 : STRIP_W;
@@ -279,10 +344,27 @@ int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, 
         blocks = (int64_t)tm * tn;
     }
     PB_CHECK(blocks < (1ll << 31), PB_ERR_INVALID, "gemm_nt: too many tiles");
-    gemm_nt_kernel<<<(unsigned)blocks, THREADS, SMEM_BYTES, stream>>>(mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha,
-                                                                      beta, lower_only ? 1 : 0, tn);
+    gemm_nt_kernel<CF><<<(unsigned)blocks, CF::THREADS, CF::SMEM_BYTES, stream>>>(
+        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only ? 1 : 0, tn);
     PB_CUDA(cudaGetLastError());
     return PB_OK;
+}
+
+}  // namespace
+
+int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
+    if (M <= 0 || N <= 0) return PB_OK;
+    PB_CHECK(K > 0, PB_ERR_INVALID, "gemm_nt: K must be positive");
+    PB_CHECK(alpha != 0.0, PB_ERR_INVALID, "gemm_nt: alpha must be non-zero");
+    PB_CHECK(!lower_only || M == N, PB_ERR_INVALID, "gemm_nt: lower_only needs a square C");
+    PB_CHECK(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), PB_ERR_INVALID, "gemm_nt: dimension too large");
+    // Small problems (panel factorisation, leaf TRSMs) would occupy only a handful of SMs with
+    // 128x64 tiles: give them 64x64 tiles so that twice as many CTAs share the work.
+    const int64_t main_tiles = ceil_div<int64_t>(M, 128) * ceil_div<int64_t>(N, 64) / (lower_only ? 2 : 1);
+    if (N <= 64 || M <= 64 || main_tiles < 2 * num_sms())
+        return launch<CfgSmall>(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
+    return launch<CfgMain>(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only);
 }
 
 }  // namespace pb

@@ -5,12 +5,15 @@
 //
 //   for each block column k (width NB):
 //     1. diagonal block: recursive potrf down to 64x64 leaves; a leaf is one CTA that factors the
-//        block with register-resident rows and warp shuffles (32x32 at a time) and also emits the
-//        inverse of the leaf (used by every TRSM as a GEMM operand);
+//        block held in registers (4x4 per thread), exchanging one pivot column per step through
+//        shared memory, and also emits the inverse of the leaf (the TRSMs use it as a GEMM operand);
 //     2. panel TRSM  P <- P L_kk^{-T}: recursive, every flop is a DMMA GEMM (gemm_dmma.cu);
 //     3. trailing SYRK  A22 -= P P^T on lower tiles only (DMMA GEMM, K = NB).
 //   All launches are asynchronous on one stream; failure (non-positive pivot) lands in *info.
 #include "common.cuh"
+#include <mutex>
+#include <vector>
+#include <cstdlib>
 
 namespace pb {
 
@@ -19,150 +22,110 @@ namespace {
 constexpr int LEAF = 64;
 constexpr int LDS = LEAF + 1;   // padded smem leading dimension
 
-// Factor a 32x32 SPD block held one row per lane (a[k] = A[lane][k], lower part valid).
-// On exit a[k] = L[lane][k] for k <= lane.  Returns false if a pivot was not positive.
-__device__ __forceinline__ bool warp_potrf32(double (&a)[32], int lane, int& bad_col) {
-    bool ok = true;
-    bad_col = -1;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(d > 0.0) && ok) { ok = false; bad_col = j; }
-        const double r = 1.0 / sqrt(d);
-        const double l = (lane == j) ? sqrt(d) : a[j] * r;
-        a[j] = l;
-#pragma unroll
-        for (int k = j + 1; k < 32; ++k) {
-            const double lk = __shfl_sync(0xffffffffu, l, k);
-            a[k] = fma(-l, lk, a[k]);
-        }
-    }
-    return ok;
-}
-
-// One CTA (256 threads): factor the nv x nv (nv <= 64) diagonal block at A (lda) in place and
-// write the 64x64 inverse of the (identity-padded) factor to Dinv (row-major, ld 64).
+// One CTA (256 threads): factor the nv x nv (nv <= 64) diagonal block at A (lda) in place and write
+// the 64x64 inverse of the (identity-padded) factor to Dinv (row-major, ld 64).
+//
+// Right-looking, register-resident: thread (ti, tk) = (tid/16, tid%16) owns the 4x4 elements
+// (ti + 16a, tk + 16b) of the (symmetrised) block in registers for the whole factorisation.  Each of
+// the 64 steps publishes one column through a double-buffered shared-memory vector (one
+// __syncthreads per step), forms the pivot's reciprocal square root once per thread, and applies the
+// rank-1 update to the register tile.  All loops are rolled: the kernel is ~1.5k instructions, so it
+// stays inside the instruction cache (a fully unrolled warp-shuffle variant was 27k instructions and
+// ran 94 us per leaf, instruction-fetch bound).
+// The inverse is then built row by row (left-looking forward substitution, 4 threads per column).
 __global__ void __launch_bounds__(256, 1)
 potrf_leaf_kernel(double* __restrict__ A, int64_t lda, int nv, double* __restrict__ Dinv, int32_t* info, int col0) {
     extern __shared__ double leaf_smem[];
-    double* S = leaf_smem;                  // working block -> L
-    double* V = leaf_smem + LEAF * LDS;     // inverse
-    double* rd = V + LEAF * LDS;            // reciprocal diagonal of L
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    double* Ls = leaf_smem;                                   // the factor L          [64][65]
+    double* Vs = Ls + LEAF * LDS;                             // its inverse           [64][65]
+    double (*col)[LEAF] = reinterpret_cast<double (*)[LEAF]>(Vs + LEAF * LDS);   // published pivot column [2][64]
+    double* rdiag = Vs + LEAF * LDS + 2 * LEAF;               // 1 / L_jj              [64]
+    const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
 
-    for (int e = tid; e < LEAF * LEAF; e += 256) {
-        const int i = e >> 6, k = e & 63;
-        double v = 0.0;
-        if (i < nv && k <= i) v = A[(int64_t)i * lda + k];
-        else if (i == k) v = 1.0;
-        S[i * LDS + k] = v;
-        V[i * LDS + k] = 0.0;
+    double reg[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int i = ti + 16 * a, k = tk + 16 * b;
+            const int r = i > k ? i : k, c = i > k ? k : i;        // symmetrise from the stored lower triangle
+            double v = (i == k) ? 1.0 : 0.0;                      // identity padding beyond nv
+            if (r < nv) v = A[(int64_t)r * lda + c];
+            reg[a][b] = v;
+        }
+    for (int e = tid; e < LEAF * LDS; e += 256) Ls[e] = 0.0;
+    if (tk == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) col[0][ti + 16 * a] = reg[a][0];
     }
     __syncthreads();
 
-    // --- L11 = chol(A11) : warp 0, rows in registers, pivots/columns exchanged by shuffle ---
-    if (warp == 0) {
-        double a[32];
+    for (int j = 0; j < LEAF; ++j) {
+        const double* cb = col[j & 1];
+        const double d = cb[j];
+        if (tid == 0 && !(d > 0.0)) atomicCAS(info, 0, col0 + j + 1);
+        const double rinv = rsqrt(d);
+        const double rd = rinv * rinv;
+        double ci[4], ck[4];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) a[k] = S[lane * LDS + k];
-        int bad;
-        if (!warp_potrf32(a, lane, bad) && lane == 0) atomicCAS(info, 0, col0 + bad + 1);
+        for (int a = 0; a < 4; ++a) ci[a] = cb[ti + 16 * a];
 #pragma unroll
-        for (int k = 0; k < 32; ++k) S[lane * LDS + k] = (k <= lane) ? a[k] : 0.0;
-        __syncwarp();
-        rd[lane] = 1.0 / S[lane * LDS + lane];
-    }
-    __syncthreads();
-
-    // --- A21 <- A21 L11^{-T} : warp 1, one row per lane, column-oriented substitution ---
-    if (warp == 1) {
-        double b[32];
+        for (int b = 0; b < 4; ++b) ck[b] = cb[tk + 16 * b];
+        if (tk == (j & 15)) {                                      // owners of column j emit L[:, j]
 #pragma unroll
-        for (int k = 0; k < 32; ++k) b[k] = S[(32 + lane) * LDS + k];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const double x = b[c] * rd[c];
-            b[c] = x;
-#pragma unroll
-            for (int k = c + 1; k < 32; ++k) b[k] = fma(-x, S[k * LDS + c], b[k]);
+            for (int a = 0; a < 4; ++a) {
+                const int i = ti + 16 * a;
+                if (i > j) Ls[i * LDS + j] = ci[a] * rinv;
+                else if (i == j) { Ls[i * LDS + j] = d * rinv; rdiag[j] = rinv; }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 32; ++k) S[(32 + lane) * LDS + k] = b[k];
+        for (int a = 0; a < 4; ++a) {
+            const double t = ci[a] * rd;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) reg[a][b] = fma(-t, ck[b], reg[a][b]);
+        }
+        if (j + 1 < LEAF && tk == ((j + 1) & 15)) {                // publish column j+1
+            const int bsel = (j + 1) >> 4;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                double v = reg[a][0];
+#pragma unroll
+                for (int b = 1; b < 4; ++b) v = (bsel == b) ? reg[a][b] : v;
+                col[(j + 1) & 1][ti + 16 * a] = v;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
-    // --- A22 -= A21 A21^T (lower) : all threads, 4 elements each ---
-    for (int e = tid; e < 32 * 32; e += 256) {
-        const int i = e >> 5, j = e & 31;
-        if (j <= i) {
+    // write the factor back (lower triangle of the valid part only)
+    for (int e = tid; e < LEAF * LEAF; e += 256) {
+        const int i = e >> 6, k = e & 63;
+        if (i < nv && k <= i) A[(int64_t)i * lda + k] = Ls[i * LDS + k];
+    }
+
+    // inverse V = L^{-1}: column c handled by 4 threads (q = k mod 4 slices of the dot product);
+    // V is accumulated in place of the register tile's smem image: Vs[i][c].
+    {
+        const int c = tid >> 2, q = tid & 3;
+        for (int i = 0; i < LEAF; ++i) {
             double s = 0.0;
-#pragma unroll 8
-            for (int k = 0; k < 32; ++k) s = fma(S[(32 + i) * LDS + k], S[(32 + j) * LDS + k], s);
-            S[(32 + i) * LDS + 32 + j] -= s;
+            for (int k = c + q; k < i; k += 4) s = fma(Ls[i * LDS + k], Vs[k * LDS + c], s);   // V[k][c] = 0 for k < c
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0) Vs[i * LDS + c] = (i < c) ? 0.0 : ((i == c ? 1.0 : 0.0) - s) * rdiag[i];
+            __syncwarp();          // the 4 threads of a column live in one warp; columns are independent
         }
     }
     __syncthreads();
-
-    // --- L22 = chol(A22) : warp 0 ---
-    if (warp == 0) {
-        double a[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) a[k] = S[(32 + lane) * LDS + 32 + k];
-        int bad;
-        if (!warp_potrf32(a, lane, bad) && lane == 0) atomicCAS(info, 0, col0 + 32 + bad + 1);
-#pragma unroll
-        for (int k = 0; k < 32; ++k) S[(32 + lane) * LDS + 32 + k] = (k <= lane) ? a[k] : 0.0;
-        __syncwarp();
-        rd[32 + lane] = 1.0 / S[(32 + lane) * LDS + 32 + lane];
-    }
-    __syncthreads();
-
-    // --- inverses of the two diagonal 32x32 factors: warp 0 -> inv(L11), warp 1 -> inv(L22);
-    //     lane = column j of the inverse, column-oriented forward substitution on e_j ---
-    if (warp < 2) {
-        const int o = warp * 32;
-        double b[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) b[k] = (k == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const double x = b[c] * rd[o + c];
-            b[c] = x;
-#pragma unroll
-            for (int k = c + 1; k < 32; ++k) b[k] = fma(-x, S[(o + k) * LDS + o + c], b[k]);
-        }
-#pragma unroll
-        for (int k = 0; k < 32; ++k) V[(o + k) * LDS + o + lane] = b[k];
-    }
-    __syncthreads();
-
-    // --- inv21 = -inv22 * (L21 * inv11): two 32^3 products through a temporary in the (unused)
-    //     upper-right quadrant of V ---
-    for (int e = tid; e < 32 * 32; e += 256) {
-        const int i = e >> 5, j = e & 31;
-        double s = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) s = fma(S[(32 + i) * LDS + k], V[k * LDS + j], s);
-        V[i * LDS + 32 + j] = s;     // T = L21 * inv11 (parked in the upper-right quadrant)
-    }
-    __syncthreads();
-    for (int e = tid; e < 32 * 32; e += 256) {
-        const int i = e >> 5, j = e & 31;
-        double s = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) s = fma(V[(32 + i) * LDS + 32 + k], V[k * LDS + 32 + j], s);
-        V[(32 + i) * LDS + j] = -s;
-    }
-    __syncthreads();
-
     for (int e = tid; e < LEAF * LEAF; e += 256) {
         const int i = e >> 6, k = e & 63;
-        if (i < nv && k <= i) A[(int64_t)i * lda + k] = S[i * LDS + k];
-        Dinv[e] = (k <= i) ? V[i * LDS + k] : 0.0;
+        Dinv[e] = (k <= i) ? Vs[i * LDS + k] : 0.0;
     }
 }
 
-constexpr int LEAF_SMEM = (2 * LEAF * LDS + LEAF) * 8;
+
+constexpr int LEAF_SMEM = (2 * LEAF * LDS + 3 * LEAF) * 8;
 
 struct Ctx {
     cudaStream_t stream;
@@ -209,29 +172,130 @@ int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
 }  // namespace
 
 int potrf_block_size(int64_t n) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("PB_POTRF_NB");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced > 0) return forced / 64 * 64 > 0 ? forced / 64 * 64 : 64;
     if (n <= 2048) return 256;
     return 512;
 }
 
+namespace {
+
+// Highest-priority non-blocking side stream (one per device) for the look-ahead panel work.
+int side_stream(cudaStream_t* out) {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    PB_CHECK(dev >= 0 && dev < 64, PB_ERR_INVALID, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev]) {
+        int lo = 0, hi = 0;
+        PB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        PB_CUDA(cudaStreamCreateWithPriority(&streams[dev], cudaStreamNonBlocking, hi));
+    }
+    *out = streams[dev];
+    return PB_OK;
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> evs;
+    ~EventPool() { for (cudaEvent_t e : evs) cudaEventDestroy(e); }
+    int get(cudaEvent_t* e) {
+        PB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        evs.push_back(*e);
+        return PB_OK;
+    }
+};
+
+bool lookahead_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PB_POTRF_LOOKAHEAD");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+}  // namespace
+
+// Right-looking blocked factorisation with one-panel look-ahead.
+//   main stream : trailing SYRK of step k restricted to the columns right of panel k+1
+//   side stream : (a) update of panel k+1's block column with panel k, (b) factorisation of panel k+1
+// so the latency-bound panel chain (leaf kernels, small GEMMs) runs underneath the big SYRK.
 int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
           int32_t* info) {
     PB_CHECK(n >= 0 && lda >= n, PB_ERR_INVALID, "potrf: bad n/lda");
     PB_CHECK(workspace_bytes >= pb_potrf_workspace_bytes(n), PB_ERR_INVALID, "potrf: workspace too small");
     PB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
     if (n == 0) return PB_OK;
-    Ctx c{stream, lda, reinterpret_cast<double*>(workspace), info};
     const int64_t NB = potrf_block_size(n);
-    for (int64_t k0 = 0; k0 < n; k0 += NB) {
-        const int64_t nb = n - k0 < NB ? n - k0 : NB;
-        double* Akk = A + k0 * lda + k0;
-        PB_TRY(potrf_rec(c, Akk, nb, k0));
-        const int64_t m = n - k0 - nb;
-        if (m > 0) {
-            double* P = A + (k0 + nb) * lda + k0;
-            PB_TRY(trsm_rec(c, P, lda, m, Akk, nb, k0));
-            PB_TRY(gemm_nt(stream, m, m, nb, -1.0, P, lda, P, lda, 1.0, P + nb, lda, true));
+    Ctx cm{stream, lda, reinterpret_cast<double*>(workspace), info};
+
+    if (!lookahead_enabled() || n <= 2 * NB) {
+        for (int64_t k0 = 0; k0 < n; k0 += NB) {
+            const int64_t nb = n - k0 < NB ? n - k0 : NB;
+            double* Akk = A + k0 * lda + k0;
+            PB_TRY(potrf_rec(cm, Akk, nb, k0));
+            const int64_t m = n - k0 - nb;
+            if (m > 0) {
+                double* P = A + (k0 + nb) * lda + k0;
+                PB_TRY(trsm_rec(cm, P, lda, m, Akk, nb, k0));
+                PB_TRY(gemm_nt(stream, m, m, nb, -1.0, P, lda, P, lda, 1.0, P + nb, lda, true));
+            }
         }
+        return PB_OK;
     }
+
+    cudaStream_t side;
+    PB_TRY(side_stream(&side));
+    Ctx cs{side, lda, reinterpret_cast<double*>(workspace), info};
+    EventPool pool;
+    cudaEvent_t ev_panel, ev_trail = nullptr, ev_start;
+
+    // panel 0 on the main stream
+    {
+        const int64_t nb = n < NB ? n : NB;
+        PB_TRY(potrf_rec(cm, A, nb, 0));
+        PB_TRY(trsm_rec(cm, A + nb * lda, lda, n - nb, A, nb, 0));
+        PB_TRY(pool.get(&ev_panel));
+        PB_CUDA(cudaEventRecord(ev_panel, stream));
+    }
+    (void)ev_start;
+    for (int64_t k0 = 0; k0 + NB < n; k0 += NB) {
+        const int64_t nb = NB;                       // panel k is full width here (there are rows below it)
+        const int64_t k1 = k0 + nb;                  // first row/col of panel k+1
+        const int64_t nb1 = n - k1 < NB ? n - k1 : NB;
+        const int64_t k2 = k1 + nb1;                 // first row/col right of panel k+1
+        const int64_t m2 = n - k2;
+        double* P1 = A + k1 * lda + k0;              // rows of panel k belonging to block row k+1 (nb1 x nb)
+        double* P2 = A + k2 * lda + k0;              // rows of panel k below that (m2 x nb)
+
+        // ---- side: bring block column k+1 up to date with panel k, then factor it ----
+        PB_CUDA(cudaStreamWaitEvent(side, ev_panel, 0));
+        if (ev_trail) PB_CUDA(cudaStreamWaitEvent(side, ev_trail, 0));
+        double* A11 = A + k1 * lda + k1;
+        PB_TRY(gemm_nt(side, nb1, nb1, nb, -1.0, P1, lda, P1, lda, 1.0, A11, lda, true));
+        if (m2 > 0) PB_TRY(gemm_nt(side, m2, nb1, nb, -1.0, P2, lda, P1, lda, 1.0, A + k2 * lda + k1, lda, false));
+        PB_TRY(potrf_rec(cs, A11, nb1, k1));
+        if (m2 > 0) PB_TRY(trsm_rec(cs, A + k2 * lda + k1, lda, m2, A11, nb1, k1));
+        cudaEvent_t ev_next;
+        PB_TRY(pool.get(&ev_next));
+        PB_CUDA(cudaEventRecord(ev_next, side));
+
+        // ---- main: the rest of the trailing update with panel k ----
+        PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
+        if (m2 > 0) {
+            PB_TRY(gemm_nt(stream, m2, m2, nb, -1.0, P2, lda, P2, lda, 1.0, A + k2 * lda + k2, lda, true));
+            PB_TRY(pool.get(&ev_trail));
+            PB_CUDA(cudaEventRecord(ev_trail, stream));
+        }
+        ev_panel = ev_next;
+    }
+    PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
     return PB_OK;
 }
 

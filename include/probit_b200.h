@@ -76,6 +76,13 @@ typedef struct pb_likelihood_spec {
 int pb_version(void);
 const char* pb_last_error(void);
 
+/* Measurement hooks used by bench.py: total kernel launches issued by this library so far, and
+ * CUDA-event timing (on the launching stream) of the trailing-update GEMM kernel between
+ * pb_profile_begin() and pb_profile_end() (call the latter after a device synchronise).        */
+long long pb_launch_count(void);
+int pb_profile_begin(void);
+int pb_profile_end(long long* gemm_launches, double* gemm_ms, double* gemm_flops);
+
 /* ---- K4: fused per-datum likelihood (value, gradient, Hessian, third derivative) --------------
  * probit/approximators.py:96-104.  y is int64 class labels (ordinal) or f64 targets (Gaussian).
  * Any of ll/g/h/d3 may be NULL.  `batch` independent f-vectors of length n share y (the restart

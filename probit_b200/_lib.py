@@ -52,6 +52,9 @@ _SPEC, _LIK, _PROB = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER
 SIGNATURES = {
     "pb_version": (_i32, []),
     "pb_last_error": (C.c_char_p, []),
+    "pb_launch_count": (C.c_longlong, []),
+    "pb_profile_begin": (_i32, []),
+    "pb_profile_end": (_i32, [C.POINTER(C.c_longlong), C.POINTER(_f64), C.POINTER(_f64)]),
     "pb_likelihood": (_i32, [_p, _LIK, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "pb_predictive_distributions": (_i32, [_p, _LIK, _p, _p, _i64, _p]),
     "pb_feature_dim": (_i32, [_SPEC, _i32]),

@@ -138,7 +138,7 @@ logdet_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __re
 
 int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y) {
     if (rows == 0) return PB_OK;
-    gemv_kernel<<<(unsigned)ceil_div<int64_t>(rows, 4), 256, 0, stream>>>(A, rows, cols, lda, x, y);
+    gemv_kernel<<<(unsigned)ceil_div<int64_t>(rows, 4), 256, 0, stream>>>(A, rows, cols, lda, x, y); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -153,13 +153,13 @@ int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const dou
             const int64_t j0 = jb * LEAF;
             const int64_t below = n - j0 - LEAF;
             const unsigned grid = below > 0 ? (unsigned)ceil_div<int64_t>(below, 256) : 1u;
-            trsv_fwd_step_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, dinv + jb * LEAF * LEAF, j0, rhs, x);
+            trsv_fwd_step_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, dinv + jb * LEAF * LEAF, j0, rhs, x); pb::note_launch();
         }
     } else {
         for (int64_t jb = nblk - 1; jb >= 0; --jb) {
             const int64_t j0 = jb * LEAF;
             const unsigned grid = j0 > 0 ? (unsigned)ceil_div<int64_t>(j0, 256) : 1u;
-            trsv_bwd_step_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, dinv + jb * LEAF * LEAF, j0, rhs, x);
+            trsv_bwd_step_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, dinv + jb * LEAF * LEAF, j0, rhs, x); pb::note_launch();
         }
     }
     PB_CUDA(cudaGetLastError());
@@ -167,7 +167,7 @@ int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const dou
 }
 
 int logdet_chol(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* out) {
-    logdet_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, out);
+    logdet_kernel<<<1, 1024, 0, stream>>>(L, n, ldl, out); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

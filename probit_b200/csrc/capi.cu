@@ -1,6 +1,9 @@
 // Error reporting and version entry points of the C ABI.
 #include "common.cuh"
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace pb {
 
@@ -13,7 +16,49 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_profiling{0};
+static std::mutex g_prof_mu;
+struct GemmRec { cudaEvent_t e0, e1; double flops; };
+static std::vector<GemmRec> g_gemm;
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool profiling_enabled() { return g_profiling.load(std::memory_order_relaxed) != 0; }
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops) {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    g_gemm.push_back({e0, e1, flops});
+}
+
 }  // namespace pb
+
+extern "C" long long pb_launch_count(void) { return pb::g_launches.load(); }
+
+extern "C" int pb_profile_begin(void) {
+    std::lock_guard<std::mutex> lock(pb::g_prof_mu);
+    for (auto& r : pb::g_gemm) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    pb::g_gemm.clear();
+    pb::g_profiling.store(1);
+    return PB_OK;
+}
+
+// Caller must have synchronised the device.  Returns the number of profiled main-config GEMM launches,
+// their summed CUDA-event duration (ms) and their summed algorithmic flops.
+extern "C" int pb_profile_end(long long* gemm_launches, double* gemm_ms, double* gemm_flops) {
+    pb::g_profiling.store(0);
+    std::lock_guard<std::mutex> lock(pb::g_prof_mu);
+    double ms = 0, fl = 0;
+    for (auto& r : pb::g_gemm) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; fl += r.flops; }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    if (gemm_launches) *gemm_launches = (long long)pb::g_gemm.size();
+    if (gemm_ms) *gemm_ms = ms;
+    if (gemm_flops) *gemm_flops = fl;
+    pb::g_gemm.clear();
+    return PB_OK;
+}
 
 extern "C" int pb_version(void) { return 100; }
 

@@ -13,6 +13,12 @@ namespace pb {
 // thread-local message behind pb_last_error()
 void set_error(const char* fmt, ...);
 
+// profiling hooks (capi.cu): every kernel launch of the library is counted; when profiling is on the
+// trailing-update GEMM launches are bracketed by CUDA events on their own stream.
+void note_launch();
+bool profiling_enabled();
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops);
+
 #define PB_CUDA(expr)                                                                         \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \

@@ -238,7 +238,7 @@ int build_gram(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
 }
 
 int finalize(cudaStream_t st, const Ws& ws, unsigned nblk, double* out0, double* out1) {
-    finalize_kernel<<<1, 256, 0, st>>>(ws.partial(), (int)nblk, out0, out1);
+    finalize_kernel<<<1, 256, 0, st>>>(ws.partial(), (int)nblk, out0, out1); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -257,7 +257,7 @@ int posterior_stats(cudaStream_t st, const pb_problem* prob, const lik::Params& 
     PB_TRY(gemv(st, ws.K(), n, n, ws.L.ld, w, ws.vec(V_F)));
     const unsigned nb = vec_blocks(n);
     posterior_stats_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, w, n, prec_out,
-                                               ws.partial());
+                                               ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_FTW);
 }
@@ -318,15 +318,15 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
         else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
         laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_S),
-                                                ws.vec(V_B), ws.partial());
+                                                ws.vec(V_B), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
         PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));
         PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));       // K b
-        mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C));
+        mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C)); pb::note_launch();
         PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
         PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
-        newton_update_kernel<<<nb, 256, 0, st>>>(ws.vec(V_B), ws.vec(V_S), ws.vec(V_C), w, n, wn, ws.partial());
+        newton_update_kernel<<<nb, 256, 0, st>>>(ws.vec(V_B), ws.vec(V_S), ws.vec(V_C), w, n, wn, ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_ERR2, nullptr));
         PB_TRY(read_scalars(st, ws, host, &info_host));
@@ -359,7 +359,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         // chol(K + diag(1/p) + jitter I) of objective_LA (Laplace.py:24) in its B form:
         // sum log diag L_cov + 0.5 sum log p == sum log diag chol(I + s s^T o (K + jitter I))
         const unsigned nb2 = vec_blocks(n);
-        sqrt_kernel<<<nb2, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial());
+        sqrt_kernel<<<nb2, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb2, nullptr, ws.scalars() + S_BAD));
         PB_TRY(factor_B(st, ws, n, ws.vec(V_S), jitter));
@@ -414,11 +414,11 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
     while (error > tolerance && it < maxiter) {
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));
         else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
-        vb_rhs_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_B));
+        vb_rhs_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_B)); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_B), ws.vec(V_X)));     // cholesky_solve (VB.py:11)
         PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), wn));
-        diff_norm_kernel<<<nb, 256, 0, st>>>(wn, w, n, ws.partial());
+        diff_norm_kernel<<<nb, 256, 0, st>>>(wn, w, n, ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_ERR2, nullptr));
         PB_TRY(read_scalars(st, ws, host, nullptr));
@@ -433,7 +433,7 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
         double* tmp = w; w = wn; wn = tmp;
     }
     PB_TRY(posterior_stats(st, prob, lp, ws, w, nullptr));
-    fill_kernel<<<nb, 256, 0, st>>>(precision, n, 1.0 / (sigma * sigma));     // approximators.py:339
+    fill_kernel<<<nb, 256, 0, st>>>(precision, n, 1.0 / (sigma * sigma)); pb::note_launch();     // approximators.py:339
     PB_CUDA(cudaMemcpyAsync(weight, w, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (posterior_mean)
         PB_CUDA(cudaMemcpyAsync(posterior_mean, ws.vec(V_F), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -455,7 +455,7 @@ extern "C" int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, co
     if (!reuse_gram) PB_TRY(build_gram(st, prob, ws));
     PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
     const unsigned nb = vec_blocks(n);
-    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial());
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, nullptr, ws.scalars() + S_BAD));
     PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));       // K + diag(1/p) (approximators.py:175) in B form
@@ -505,7 +505,7 @@ extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void
             // var = k** - || L_B^{-1} (s o k_*) ||^2  ==  Kss - einsum(Kfs, solve(K + P^-1, Kfs)) (approximators.py:175-178)
             PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, Df, Df, V, ld, ws.vec(V_S)));
             PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), V, m, ld));
-            row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, st>>>(V, m, n, ld, kss, variance + r0);
+            row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, st>>>(V, m, n, ld, kss, variance + r0); pb::note_launch();
             PB_CUDA(cudaGetLastError());
         }
     }

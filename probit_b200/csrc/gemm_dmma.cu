@@ -8,7 +8,7 @@
 // Design
 //  * CTA tile 128x64 (two CTAs per SM), K step 16 doubles (= one 128-byte TMA swizzle span).
 //  * Thread 0 drives a STAGES-deep ring of TMA box loads (cp.async.bulk.tensor.2d, SWIZZLE_128B)
-//    signalled through mbarriers (full/empty pairs), keeping STAGES-1 loads in flight.
+//    signalled through mbarriers (full/empty pairs), keeping up to STAGES loads in flight.
 //  * Eight warps (4 x 2), warp tile 32x32 -> 16 m8n8k4 accumulators (32 doubles/lane).
 //  * Bank-conflict-free fragment loads under the 128B swizzle: the 8 rows of an m8 fragment are
 //    taken in the order perm(g) = 2*(g&3) + (g>>2), so the 16 lanes of each LDS.64 phase touch
@@ -73,6 +73,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile(
@@ -166,7 +179,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     __syncthreads();
 
-    // ===== TMA producer duty: thread 0 keeps STAGES-1 loads in flight from inside the consumer loop.
+    // ===== TMA producer duty: thread 0 keeps up to STAGES loads in flight from inside the consumer loop.
     // (A dedicated 9th producer warp would put 3 warps on one SM sub-partition and cap every thread
     // at 168 registers — the register file is 16K per sub-partition — which spills the 128-register
     // accumulator tile; with 8 warps the cap is 255.)
@@ -178,9 +191,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tma_load_2d(dstA, &mapA, kb * BK, m0, full);
         tma_load_2d(dstA + A_STAGE_BYTES, &mapB, kb * BK, n0, full);
     };
+    int next_kb = kblocks < STAGES ? kblocks : STAGES;             // first k-block not yet requested (thread 0)
     if (threadIdx.x == 0) {
-        const int pre = kblocks < STAGES - 1 ? kblocks : STAGES - 1;
-        for (int kb = 0; kb < pre; ++kb) issue_stage(kb);
+        for (int kb = 0; kb < next_kb; ++kb) issue_stage(kb);      // every stage starts out free
     }
 
     // ===== consumers =====
@@ -240,15 +253,32 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % STAGES;
-        if (threadIdx.x == 0) {
-            const int nk = kb + STAGES - 1;               // refill the stage consumed in iteration kb-1
-            if (nk < kblocks) {
-                if (kb >= 1) mbar_wait(bar_base + 8 * (STAGES + (nk % STAGES)), ((kb - 1) / STAGES) & 1);
-                issue_stage(nk);
-            }
-        }
-        __syncwarp();
         mbar_wait(bar_base + 8 * s, (kb / STAGES) & 1);
+        // Release the stage consumed in iteration kb-1 only now, behind the wait loop above.  The wait
+        // is real control flow, so every DMMA of iteration kb-1 (and therefore every LDS feeding it)
+        // has issued before this arrive.  Releasing at the end of iteration kb-1 is NOT safe: ptxas
+        // hoists the arrive above the last DMMAs, right behind the last LDS *issue*, and the TMA
+        // refill then overwrites shared memory an in-flight LDS has not read yet (observed as sporadic
+        // 32-byte fragment corruption on multi-wave grids).
+        if (kb >= 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + ((kb - 1) % STAGES)));
+            if (threadIdx.x == 0) {
+                // Refill every stage whose release has completed.  Do not stall this warp on a slow
+                // sibling unless the k-block is needed by the very next iteration.
+                while (next_kb < kblocks && next_kb <= kb - 1 + STAGES) {
+                    const uint32_t eb = bar_base + 8 * (STAGES + (next_kb % STAGES));
+                    const uint32_t par = ((next_kb / STAGES) - 1) & 1;
+                    if (!mbar_test(eb, par)) {
+                        if (next_kb > kb + 1) break;
+                        mbar_wait(eb, par);
+                    }
+                    issue_stage(next_kb);
+                    ++next_kb;
+                }
+            }
+            __syncwarp();
+        }
         const uint32_t st = smem_base + s * STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -262,8 +292,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_base + 8 * (STAGES + s));
     }
 
     // ===== epilogue: C = alpha * acc (store-only; the row/column permutation is undone here) =====
@@ -344,8 +372,20 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
         blocks = (int64_t)tm * tn;
     }
     PB_CHECK(blocks < (1ll << 31), PB_ERR_INVALID, "gemm_nt: too many tiles");
+    const bool prof = profiling_enabled() && CF::BM == 128;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        PB_CUDA(cudaEventCreate(&e0));
+        PB_CUDA(cudaEventCreate(&e1));
+        PB_CUDA(cudaEventRecord(e0, stream));
+    }
     gemm_nt_kernel<CF><<<(unsigned)blocks, CF::THREADS, CF::SMEM_BYTES, stream>>>(
-        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only ? 1 : 0, tn);
+        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only ? 1 : 0, tn); pb::note_launch();
+    if (prof) {
+        PB_CUDA(cudaEventRecord(e1, stream));
+        // algorithmic flops: 2MNK, or the lower triangle N(N+1)K for the SYRK form
+        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K);
+    }
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

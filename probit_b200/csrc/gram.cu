@@ -275,7 +275,7 @@ int features(cudaStream_t stream, const pb_kernel_spec& spec, const double* X, i
     const int64_t cap = (int64_t)num_sms() * 8;
     features_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(X, n, D, ldx, Z, ldz, spec.periodic,
                                                                              spec.stretch_in, spec.period,
-                                                                             spec.stretch_out);
+                                                                             spec.stretch_out); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -291,7 +291,7 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
         configured = true;
     }
     gram_sym_kernel<<<(unsigned)tri_tiles(n), 256, gram_smem_sym(Df), stream>>>(Z, n, Df, ldz, K, ldk, spec.base,
-                                                                           spec.scale, diag_vec, diag_scalar);
+                                                                           spec.scale, diag_vec, diag_scalar); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -309,7 +309,7 @@ int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1
     dim3 grid((unsigned)ceil_div<int64_t>(n2, TILE), (unsigned)ceil_div<int64_t>(n1, TILE));
     PB_CHECK(grid.y < 65536, PB_ERR_INVALID, "gram_cross: too many row tiles (chunk the rows)");
     gram_cross_kernel<<<grid, 256, gram_smem_cross(Df), stream>>>(Z1, n1, Z2, n2, Df, ldz1, ldz2, K, ldk, spec.base,
-                                                             spec.scale, col_scale);
+                                                             spec.scale, col_scale); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -317,7 +317,7 @@ int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1
 int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, const double* s, double a,
                   double jitter, double* B, int64_t ldb) {
     if (n == 0) return PB_OK;
-    sym_transform_kernel<<<(unsigned)tri_tiles(n), 256, 0, stream>>>(K, n, ldk, s, a, jitter, B, ldb);
+    sym_transform_kernel<<<(unsigned)tri_tiles(n), 256, 0, stream>>>(K, n, ldk, s, a, jitter, B, ldb); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

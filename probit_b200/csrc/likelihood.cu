@@ -63,7 +63,7 @@ int likelihood(cudaStream_t stream, const pb_likelihood_spec& spec, const double
     const int64_t want = ceil_div<int64_t>(total, 256);
     const int64_t cap = (int64_t)num_sms() * 8;
     likelihood_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p, f, y, n, total, spec.cutpoints, ll, g,
-                                                                               h, d3);
+                                                                               h, d3); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -78,7 +78,7 @@ extern "C" int pb_predictive_distributions(pb_stream_t stream, const pb_likeliho
     const int64_t want = pb::ceil_div<int64_t>(n_test, 256);
     const int64_t cap = (int64_t)pb::num_sms() * 8;
     pb::predictive_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        mean, variance, n_test, lik->cutpoints, lik->J, lik->sigma, out);
+        mean, variance, n_test, lik->cutpoints, lik->J, lik->sigma, out); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -157,7 +157,7 @@ int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
             configured = true;
         }
         potrf_leaf_kernel<<<1, 256, LEAF_SMEM, c.stream>>>(A, c.lda, (int)n, c.dinv + (col0 / LEAF) * LEAF * LEAF,
-                                                           c.info, (int)col0);
+                                                           c.info, (int)col0); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         return PB_OK;
     }

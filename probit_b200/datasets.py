@@ -41,10 +41,11 @@ def generate_ordinal_data(seed, N, D, J, noise_variance, latent_sampler):
     """examples/classification.py:181-322 restricted to the training split.
 
     Returns (X, g, y, cutpoints) with y int64 in {0..J-1} and cutpoints of length J+1.
-    N must be a multiple of J (the reference builds J classes of equal size).
+    The reference builds J classes of exactly N/J points; when J does not divide N (N=65536, J=5 in
+    BASELINE configs[3]) the first N mod J classes get one extra point.
     """
-    if N % J:
-        raise ValueError("N must be a multiple of J")
+    if N < J:
+        raise ValueError("need at least one point per class")
     rng = np.random.default_rng(seed)
     X = rng.uniform(0.0, 1.0, size=(N, D))
     z = rng.standard_normal(N)
@@ -52,11 +53,13 @@ def generate_ordinal_data(seed, N, D, J, noise_variance, latent_sampler):
     g = f + np.sqrt(noise_variance) * rng.standard_normal(N)       # classification.py:241-243
     idx = np.argsort(g, kind="stable")                              # :247
     g, X = g[idx], X[idx]
-    per = N // J
+    counts = np.full(J, N // J, dtype=np.int64)
+    counts[: N % J] += 1
+    starts = np.concatenate([[0], np.cumsum(counts)])
     cutpoints = np.empty(J + 1)
     for j in range(1, J):                                           # :262-268
-        cutpoints[j] = 0.5 * (g[per * j] + g[per * j - 1])
+        cutpoints[j] = 0.5 * (g[starts[j]] + g[starts[j] - 1])
     cutpoints[0], cutpoints[-1] = -np.inf, np.inf                   # :269-270
-    y = np.repeat(np.arange(J, dtype=np.int64), per)
+    y = np.repeat(np.arange(J, dtype=np.int64), counts)
     perm = rng.permutation(N)     # de-sort the rows so that class order carries no structure
     return X[perm], g[perm], y[perm], cutpoints

@@ -86,3 +86,56 @@ def test_construct_and_precision_helpers():
     pr, m = p.precision(w, params)
     pr_ref, m_ref = o.precision(w, params)
     assert relerr(pr.cpu().numpy(), pr_ref) < 1e-11 and relerr(m.cpu().numpy(), m_ref) < 1e-13
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_path_matches_committed_fixtures(path):
+    """The CUDA path against the frozen oracle outputs (tests/golden, made by oracle/make_golden.py)."""
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    g = np.load(path)
+    family, gaussian, cls = str(g["family"]), bool(g["gaussian"]), str(g["cls"])
+    theta = tuple(g["theta"]) if g["theta"].ndim else float(g["theta"])
+    lik = (float(g["sigma"]),) if gaussian else (float(g["sigma"]), g["cutpoints"])
+    params = (theta, lik)
+    gp = getattr(PA, cls)((g["X"], g["y"]), make_prior(PK, family),
+                          PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    assert gp.last_result.iterations == int(g["iterations"])
+    assert relerr(w.cpu().numpy(), g["weight"]) < TOL and relerr(p.cpu().numpy(), g["precision"]) < TOL
+    m, v = gp.predict(g["Xs"], params, w, p)
+    assert relerr(m.cpu().numpy(), g["mean"]) < TOL and relerr(v.cpu().numpy(), g["variance"]) < TOL
+    assert abs(gp.objective()(params) - float(g["objective"])) < TOL * abs(float(g["objective"]))
+    if not gaussian:
+        P = PU.probit_predictive_distributions(lik, m, v).cpu().numpy()
+        assert np.abs(P - g["predictive"]).max() < 1e-9
+
+
+def test_full_size_properties_n65536():
+    """BASELINE configs[3] size (N=65536, D=4, Matern12): size-independent properties instead of an oracle run.
+    Gram symmetry and unit diagonal, Cholesky solve residual through the product's own symv, logdet sanity."""
+    import torch
+    from probit_b200 import kernels as PK, linalg
+    n = 65536
+    torch.manual_seed(0)
+    X = torch.rand(n, 4, dtype=torch.float64, device="cuda")
+    spec = (1.0 * PK.Matern12().stretch(1.0)).lower()
+    K = linalg.gram(spec, X)
+    rows = torch.randint(0, n, (64,), device="cuda")
+    assert torch.equal(K[rows][:, rows], K[rows][:, rows].T)                  # mirror store is exact
+    assert torch.all(K.diagonal() == 1.0)
+    A = linalg.gram(spec, X, diag_add=1.0)                                    # K + I, well conditioned
+    fac = linalg.potrf_(A)                                                    # in place: A now holds L
+    b = torch.randn(n, dtype=torch.float64, device="cuda")
+    x = linalg.cholesky_solve(fac, b)
+    r = linalg.symv(K, x) + x - b
+    assert (r.norm() / b.norm()).item() < 1e-11
+    ld = linalg.logdet_chol(fac).item()
+    assert 0.0 < ld < n * 0.5 * np.log(2.0 + 1.0) * 10
+    del K, A, fac
+    torch.cuda.empty_cache()

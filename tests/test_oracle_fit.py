@@ -1,0 +1,135 @@
+"""Pins the oracle's solver / approximator restatement — CPU only (closed forms, algebraic identities, fixtures)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from helpers import make_prior, ordinal_problem, regression_problem, relerr
+from oracle import approximators as OA, kernels as OK, solvers as OS, utilities as OU
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def test_fwd_solver_follows_jaxopt_stopping_rule():
+    # x <- 0.5 x + 1 converges to 2; error_k = |x_{k+1} - x_k| = 2^-k... stop at the first error <= tol
+    trace = []
+    z = OS.fwd_solver(lambda x: 0.5 * x + 1.0, np.zeros(1), 1e-3, trace=trace)
+    assert trace[-1] <= 1e-3 < trace[-2]
+    assert len(trace) == 11 and abs(z[0] - (2 - 2.0**-10)) < 1e-15
+    # maxiter caps the loop and the last iterate is returned
+    trace = []
+    z = OS.fwd_solver(lambda x: x + 1.0, np.zeros(1), 1e-3, maxiter=7, trace=trace)
+    assert len(trace) == 7 and z[0] == 7.0
+
+
+def test_newton_solver_on_a_linear_map_converges_in_one_step_plus_confirmation():
+    A = np.array([[0.2, 0.1], [0.0, 0.3]])
+    c = np.array([1.0, -2.0])
+    trace = []
+    z = OS.newton_solver(lambda x: A @ x + c, lambda x: A, np.zeros(2), 1e-8, trace=trace)
+    assert np.allclose(z, np.linalg.solve(np.eye(2) - A, c)) and len(trace) == 2
+
+
+def test_gaussian_laplace_is_exact_gp_regression():
+    X, y, params, family = regression_problem(0, 20)
+    gp = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_gaussian_likelihood)
+    w, p = gp.approximate_posterior(params)
+    K = make_prior(OK, family)(params[0])(X)
+    s2 = params[1][0] ** 2
+    wc = np.linalg.solve(K + s2 * np.eye(20), y)
+    assert relerr(w, wc) < 1e-12 and np.allclose(p, 1 / s2) and len(gp.trace) == 2
+    nlml = 0.5 * y @ wc + 0.5 * np.linalg.slogdet(K + s2 * np.eye(20))[1] + 10 * np.log(2 * np.pi)
+    assert abs(gp.objective()(params) - nlml) < 1e-9
+    Xs = np.linspace(-0.5, 1.5, 50)[:, None]
+    m, v = gp.predict(Xs, params, w, p)
+    Ks = make_prior(OK, family)(params[0])(X, Xs)
+    assert np.allclose(m, Ks.T @ wc) and np.allclose(v, params[0][1] - np.einsum("ij,ij->j", Ks, np.linalg.solve(K + s2 * np.eye(20), Ks)))
+
+
+@pytest.mark.parametrize("N,D,J,family", [(60, 1, 3, "eq"), (300, 4, 5, "matern12")])
+def test_lu_jacobian_and_cholesky_forms_give_the_same_iterates(N, D, J, family):
+    X, y, params, _ = ordinal_problem(N, N, D, J, family)
+    a = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood, newton_form="lu_jacobian")
+    b = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood, newton_form="cholesky_B")
+    wa, pa = a.approximate_posterior(params)
+    wb, pb = b.approximate_posterior(params)
+    assert len(a.trace) == len(b.trace)
+    assert relerr(wb, wa) < 1e-11 and relerr(pb, pa) < 1e-11
+    assert np.allclose(a.trace[:-1], b.trace[:-1], rtol=1e-8)
+    # fixed point: g(K w) = w
+    K = make_prior(OK, family)(params[0])(X)
+    assert np.linalg.norm(OU.grad_log_probit_likelihood_autodiff(K @ wa, y, params[1]) - wa) < 1e-8
+
+
+def test_objective_LA_equals_B_form():
+    X, y, params, family = ordinal_problem(3, 150, 2, 3, "eq")
+    gp = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    K = make_prior(OK, family)(params[0])(X)
+    f = K @ w
+    s = np.sqrt(p)
+    Bm = np.eye(150) + s[:, None] * (K + 1e-12 * np.eye(150)) * s[None, :]
+    b_form = -np.sum(OU.log_probit_likelihood(f, y, params[1])) + 0.5 * f @ w + np.sum(np.log(np.diag(np.linalg.cholesky(Bm))))
+    assert abs(gp.objective()(params) - b_form) < 1e-10 * abs(b_form)
+
+
+def test_vb_objective_closed_form_equals_literal():
+    X, y, params, family = ordinal_problem(5, 90, 2, 3, "eq")
+    gp = OA.VBGP((X, y), make_prior(OK, family), OU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    assert gp.trace[-1] <= 1e-5 and np.allclose(p, 1 / params[1][0] ** 2)
+    K = make_prior(OK, family)(params[0])(X)
+    s = params[1][0]
+    L = np.linalg.cholesky(s * s * np.eye(90) + K)
+    f = K @ w
+    closed = 0.5 * f @ w - 90 * np.log(s) + np.sum(np.log(np.diag(L))) - np.sum(OU.log_probit_likelihood(f, y, params[1]))
+    assert abs(gp.objective()(params) - closed) < 1e-9 * abs(closed)
+    # VB fixed point: (s^2 I + K) w = K w + s g(K w)
+    g = OU.grad_log_probit_likelihood_autodiff(f, y, params[1])
+    assert np.linalg.norm((s * s * np.eye(90) + K) @ w - (f + s * g)) < 1e-4
+
+
+def test_kernel_shim_semantics():
+    rng = np.random.default_rng(0)
+    x, y = rng.uniform(size=(7, 3)), rng.uniform(size=(5, 3))
+    d2 = ((x[:, None, :] - y[None, :, :]) ** 2).sum(-1)
+    assert np.allclose(OK.EQ()(x, y), np.exp(-0.5 * d2), rtol=1e-15)
+    assert np.allclose(OK.Matern12()(x, y), np.exp(-np.sqrt(d2)), rtol=1e-15)
+    assert np.allclose((2.5 * OK.EQ().stretch(0.7))(x, y), 2.5 * np.exp(-0.5 * d2 / 0.49), rtol=1e-14)
+    x1, y1 = rng.uniform(size=6), rng.uniform(size=4)
+    per = (1.3 * OK.EQ().stretch(0.8).periodic(0.5))(x1, y1)
+    assert np.allclose(per, 1.3 * np.exp(-2 * np.sin(np.pi * (x1[:, None] - y1[None, :]) / 0.5) ** 2 / 0.64), rtol=1e-12)
+    assert (1.3 * OK.EQ().stretch(0.8).periodic(0.5)).elwise(x1, x1).shape == (6, 1)
+    assert np.allclose((1.3 * OK.EQ()).elwise(x, x), 1.3)
+
+
+def test_expansion_form_distance_is_the_references_noise_floor():
+    """lab's pw_dists2 expansion puts O(1e-8) noise on diag(K) for Matern12 with D>1."""
+    rng = np.random.default_rng(1)
+    x = rng.uniform(size=(200, 4))
+    Kd = OK.Matern12()(x)
+    Ke = OK.Matern12()(x, dist_mode="expand")
+    assert np.all(np.diag(Kd) == 1.0)
+    noise = np.abs(np.diag(Ke) - 1.0).max()
+    assert 1e-10 < noise < 1e-6
+    assert np.abs(OK.EQ()(x) - OK.EQ()(x, dist_mode="expand")).max() < 1e-14
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_reproduces_committed_fixtures(path):
+    g = np.load(path)
+    family, gaussian, cls = str(g["family"]), bool(g["gaussian"]), str(g["cls"])
+    theta = tuple(g["theta"]) if g["theta"].ndim else float(g["theta"])
+    lik = (float(g["sigma"]),) if gaussian else (float(g["sigma"]), g["cutpoints"])
+    params = (theta, lik)
+    gp = getattr(OA, cls)((g["X"], g["y"]), make_prior(OK, family),
+                          OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    assert len(gp.trace) == int(g["iterations"])
+    assert relerr(w, g["weight"]) < 1e-11 and relerr(p, g["precision"]) < 1e-11
+    m, v = gp.predict(g["Xs"], params, w, p)
+    assert relerr(m, g["mean"]) < 1e-10 and relerr(v, g["variance"]) < 1e-10
+    assert abs(gp.objective()(params) - float(g["objective"])) < 1e-10 * abs(float(g["objective"]))
+    assert len(GOLDEN) >= 4

@@ -147,7 +147,9 @@ int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl
  * pb_laplace_fit: LaplaceGP.weight + precision (approximators.py:204-210,265-277) = Newton on
  *   g(Kw) - w = 0 with jaxopt's stopping rule (solvers.py:7-25): w0 = 0; repeat w+ = Newton(w);
  *   err = ||w+ - w||_2; until err <= tol or iters == maxiter.  Synchronises `stream` once per
- *   iteration (8-byte readback of err).  Outputs: weight w (n), precision p = -h(Kw) (n),
+ *   iteration (8-byte readback of err).  The first two Newton steps factor B = I + W^1/2 K W^1/2; later
+ *   steps solve with PCG preconditioned by the last factor (refactoring if PCG stalls; set
+ *   PB_LAPLACE_PCG=0 to factor every step).  Outputs: weight w (n), precision p = -h(Kw) (n),
  *   posterior mean f = K w (n); when `final_factor` != 0 the workspace additionally ends holding
  *   the Cholesky factor of B(w*) used by pb_laplace_objective / pb_predict.
  * pb_vb_fit: VBGP.weight + precision (approximators.py:332-339; VB.py:4-16).                     */
@@ -158,6 +160,8 @@ typedef struct pb_fit_result {
     double sum_ll;      /* sum_i ll(f_i) at the returned w */
     double ftw;         /* f^T w at the returned w */
     double logdet;      /* sum log diag chol(...) of the final factor (if computed) */
+    int32_t factorizations; /* Cholesky factorisations performed */
+    int32_t pcg_iterations; /* total PCG iterations of the Newton steps that reused a stale factor */
 } pb_fit_result;
 
 typedef struct pb_problem {

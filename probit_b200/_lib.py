@@ -27,7 +27,8 @@ class LikelihoodSpec(C.Structure):
 
 class FitResult(C.Structure):
     _fields_ = [("iterations", C.c_int32), ("info", C.c_int32), ("error", C.c_double),
-                ("sum_ll", C.c_double), ("ftw", C.c_double), ("logdet", C.c_double)]
+                ("sum_ll", C.c_double), ("ftw", C.c_double), ("logdet", C.c_double),
+                ("factorizations", C.c_int32), ("pcg_iterations", C.c_int32)]
 
 
 class Problem(C.Structure):

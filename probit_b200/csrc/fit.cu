@@ -13,6 +13,7 @@
 // (N^3/3 flops) and never divides by W.  The iterates agree with the LU form to ~1e-14
 // (tests/test_oracle_fit.py) and the iteration count is identical.
 #include "likelihood.cuh"
+#include <cstdlib>
 
 namespace pb {
 
@@ -30,8 +31,8 @@ struct Layout {
     int64_t vec_stride;   // doubles per vector slot
 };
 
-enum VecSlot { V_W = 0, V_WN, V_F, V_S, V_B, V_T, V_C, V_X, V_G, V_COUNT };
-enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_COUNT = 8 };
+enum VecSlot { V_W = 0, V_WN, V_F, V_S, V_B, V_T, V_C, V_X, V_G, V_SF, V_E, V_R, V_Z, V_P, V_Q, V_Y, V_U, V_COUNT };
+enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_PBP, S_RZ0, S_RZ1, S_RR, S_R0, S_COUNT = 16 };
 
 Layout make_layout(int64_t n, int D) {
     Layout L;
@@ -214,6 +215,84 @@ row_sumsq_kernel(const double* __restrict__ V, int64_t rows, int64_t cols, int64
     if (lane == 0) var[r] = kss - s;
 }
 
+// ---- preconditioned CG on B x = c, B = I + s s^T o K, preconditioner = a stale Cholesky factor ----
+// (used by the later Newton iterations, where W changes little: ~15 iterations of one symv + two trsv
+// replace an N^3/3 factorisation; the solution is driven to 1e-13 relative residual, so the iterates
+// agree with the direct solve far inside the 1e-8 parity tolerance.)
+
+// e_i = clamp(s_fac_i / s_i): M^{-1} = E B_fac^{-1} E is SPD for any positive diagonal E
+__global__ void __launch_bounds__(256)
+pcg_scale_kernel(const double* __restrict__ s, const double* __restrict__ sf, int64_t n, double* __restrict__ e) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        double v = (s[i] > 0.0 && sf[i] > 0.0) ? sf[i] / s[i] : 1.0;
+        e[i] = fmin(fmax(v, 0.25), 4.0);
+    }
+}
+
+// r = c, y = 0; partial: ||c||^2
+__global__ void __launch_bounds__(256)
+pcg_init_kernel(const double* __restrict__ c, int64_t n, double* __restrict__ r, double* __restrict__ y,
+                double* __restrict__ partial) {
+    double a = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = c[i];
+        r[i] = v;
+        y[i] = 0.0;
+        a = fma(v, v, a);
+    }
+    write_partials(a, 0.0, partial);
+}
+
+// out = a o b; optional partial: sum r o out (the r.z product of PCG)
+__global__ void __launch_bounds__(256)
+pcg_mul_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ r, int64_t n,
+                   double* __restrict__ out, double* __restrict__ partial) {
+    double d = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double v = a[i] * b[i];
+        out[i] = v;
+        if (r) d = fma(r[i], v, d);
+    }
+    write_partials(d, 0.0, partial);
+}
+
+// q = p + s o v (= B p); partial: p.q
+__global__ void __launch_bounds__(256)
+pcg_bp_kernel(const double* __restrict__ p, const double* __restrict__ s, const double* __restrict__ v, int64_t n,
+              double* __restrict__ q, double* __restrict__ partial) {
+    double d = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double qi = fma(s[i], v[i], p[i]);
+        q[i] = qi;
+        d = fma(p[i], qi, d);
+    }
+    write_partials(d, 0.0, partial);
+}
+
+// alpha = rz / pBp (device scalars); y += alpha p; r -= alpha q; partial: ||r||^2
+__global__ void __launch_bounds__(256)
+pcg_update_kernel(const double* __restrict__ sc_rz, const double* __restrict__ sc_pbp, const double* __restrict__ p,
+                  const double* __restrict__ q, int64_t n, double* __restrict__ y, double* __restrict__ r,
+                  double* __restrict__ partial) {
+    const double alpha = *sc_rz / *sc_pbp;
+    double d = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        y[i] = fma(alpha, p[i], y[i]);
+        const double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        d = fma(ri, ri, d);
+    }
+    write_partials(d, 0.0, partial);
+}
+
+// p = z + (rz_new / rz_old) p
+__global__ void __launch_bounds__(256)
+pcg_dir_kernel(const double* __restrict__ sc_new, const double* __restrict__ sc_old, const double* __restrict__ z,
+               int64_t n, double* __restrict__ p) {
+    const double beta = *sc_new / *sc_old;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] = fma(beta, p[i], z[i]);
+}
+
 int check_problem(const pb_problem* prob) {
     PB_CHECK(prob != nullptr, PB_ERR_INVALID, "null problem");
     PB_CHECK(prob->n >= 1 && prob->D >= 1, PB_ERR_INVALID, "problem needs n >= 1 and D >= 1");
@@ -269,6 +348,63 @@ int factor_B(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double j
     return logdet_chol(st, ws.B(), n, ws.L.ld, ws.scalars() + S_LOGDET);
 }
 
+// Solve B(s) y = c by PCG, preconditioned with the Cholesky factor currently in ws.B() (built for the
+// s stored in V_SF).  c is left intact; the solution lands in V_Y.  *iters = iterations used, or -1 if the
+// relative residual did not reach `tol` within `maxit` (the caller then refactors).  Synchronises `st`
+// once per iteration (8-byte readback of the residual norm).
+int pcg_solve(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const double* c, int maxit, double tol,
+              int* iters) {
+    const unsigned nb = vec_blocks(n);
+    const int64_t ld = ws.L.ld;
+    double* sc = ws.scalars();
+    double host[S_COUNT];
+    pcg_scale_kernel<<<nb, 256, 0, st>>>(s, ws.vec(V_SF), n, ws.vec(V_E)); pb::note_launch();
+    pcg_init_kernel<<<nb, 256, 0, st>>>(c, n, ws.vec(V_R), ws.vec(V_Y), ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_R0, nullptr));
+    auto precondition = [&](double* rz_slot) -> int {      // z = E B_fac^{-1} E r ; rz = r.z
+        pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(ws.vec(V_E), ws.vec(V_R), nullptr, n, ws.vec(V_U), ws.partial()); pb::note_launch();
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_U), ws.vec(V_Z)));
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_Z), ws.vec(V_U)));
+        pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(ws.vec(V_E), ws.vec(V_U), ws.vec(V_R), n, ws.vec(V_Z), ws.partial()); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        return finalize(st, ws, nb, rz_slot, nullptr);
+    };
+    int cur = 0;
+    PB_TRY(precondition(sc + S_RZ0));
+    PB_CUDA(cudaMemcpyAsync(ws.vec(V_P), ws.vec(V_Z), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    *iters = -1;
+    for (int j = 1; j <= maxit; ++j) {
+        pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(s, ws.vec(V_P), nullptr, n, ws.vec(V_U), ws.partial()); pb::note_launch();
+        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_U), ws.vec(V_T)));
+        pcg_bp_kernel<<<nb, 256, 0, st>>>(ws.vec(V_P), s, ws.vec(V_T), n, ws.vec(V_Q), ws.partial()); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, sc + S_PBP, nullptr));
+        pcg_update_kernel<<<nb, 256, 0, st>>>(sc + (cur ? S_RZ1 : S_RZ0), sc + S_PBP, ws.vec(V_P), ws.vec(V_Q), n,
+                                              ws.vec(V_Y), ws.vec(V_R), ws.partial()); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, sc + S_RR, nullptr));
+        PB_TRY(read_scalars(st, ws, host, nullptr));
+        if (!(host[S_RR] == host[S_RR]) || !(host[S_PBP] > 0.0)) return PB_OK;       // breakdown: let the caller refactor
+        if (host[S_RR] <= tol * tol * host[S_R0]) { *iters = j; return PB_OK; }
+        PB_TRY(precondition(sc + (cur ? S_RZ0 : S_RZ1)));
+        pcg_dir_kernel<<<nb, 256, 0, st>>>(sc + (cur ? S_RZ0 : S_RZ1), sc + (cur ? S_RZ1 : S_RZ0), ws.vec(V_Z), n,
+                                           ws.vec(V_P)); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        cur ^= 1;
+    }
+    return PB_OK;
+}
+
+bool pcg_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PB_LAPLACE_PCG");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 }  // namespace
 }  // namespace pb
 
@@ -314,6 +450,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
     int it = 0;
     double* w = ws.vec(V_W);
     double* wn = ws.vec(V_WN);
+    bool have_factor = false;
     while (error > tolerance && it < maxiter) {                             // jaxopt loop (solvers.py:13-14)
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
         else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
@@ -321,12 +458,30 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
                                                 ws.vec(V_B), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
-        PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));
         PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));       // K b
         mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C)); pb::note_launch();
-        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
-        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
-        newton_update_kernel<<<nb, 256, 0, st>>>(ws.vec(V_B), ws.vec(V_S), ws.vec(V_C), w, n, wn, ws.partial()); pb::note_launch();
+        // x = B^{-1} (s o K b).  The first two iterations factor B (W moves a lot from f = 0); later ones
+        // reuse the last factor as a PCG preconditioner and refactor only if PCG stalls.
+        const double* xsol = ws.vec(V_C);
+        bool solved = false;
+        if (have_factor && it >= 2 && pcg_enabled()) {
+            int used = -1;
+            PB_TRY(pcg_solve(st, ws, n, ws.vec(V_S), ws.vec(V_C), 60, 1e-13, &used));
+            if (used >= 0) {
+                solved = true;
+                xsol = ws.vec(V_Y);
+                result_host->pcg_iterations += used;
+            }
+        }
+        if (!solved) {
+            PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));
+            PB_CUDA(cudaMemcpyAsync(ws.vec(V_SF), ws.vec(V_S), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            have_factor = true;
+            result_host->factorizations += 1;
+            PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
+            PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
+        }
+        newton_update_kernel<<<nb, 256, 0, st>>>(ws.vec(V_B), ws.vec(V_S), xsol, w, n, wn, ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_ERR2, nullptr));
         PB_TRY(read_scalars(st, ws, host, &info_host));
@@ -363,6 +518,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb2, nullptr, ws.scalars() + S_BAD));
         PB_TRY(factor_B(st, ws, n, ws.vec(V_S), jitter));
+        result_host->factorizations += 1;
     }
     PB_TRY(read_scalars(st, ws, host, &info_host));
     result_host->sum_ll = host[S_SUMLL];
@@ -398,6 +554,7 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
     PB_TRY(potrf(st, ws.B(), n, ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info()));
     PB_TRY(logdet_chol(st, ws.B(), n, ld, ws.scalars() + S_LOGDET));
     PB_CUDA(cudaMemsetAsync(ws.vec(V_W), 0, n * sizeof(double), st));
+    result_host->factorizations = 1;
 
     double host[S_COUNT];
     int32_t info_host = 0;

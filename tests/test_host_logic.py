@@ -28,7 +28,7 @@ def test_struct_layouts_match_the_header():
     from probit_b200 import _lib
     assert ctypes.sizeof(_lib.KernelSpec) == 40
     assert ctypes.sizeof(_lib.LikelihoodSpec) == 40
-    assert ctypes.sizeof(_lib.FitResult) == 40
+    assert ctypes.sizeof(_lib.FitResult) == 48
     assert ctypes.sizeof(_lib.Problem) == 32 + 40 + 40
     assert _lib.Problem.kernel.offset == 32 and _lib.Problem.lik.offset == 72
 

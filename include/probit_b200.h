@@ -75,6 +75,10 @@ typedef struct pb_likelihood_spec {
 
 int pb_version(void);
 const char* pb_last_error(void);
+/* Tunables: "laplace_pcg_min_n" (smallest N at which late Newton steps use stale-factor PCG instead of a
+ * fresh factorisation; default 24576, 0 = always, huge = never), "potrf_block" (panel width, 0 = auto),
+ * "potrf_lookahead" (0/1). */
+int pb_set_option(const char* name, double value);
 
 /* Measurement hooks used by bench.py: total kernel launches issued by this library so far, and
  * CUDA-event timing (on the launching stream) of the trailing-update GEMM kernel between
@@ -148,8 +152,8 @@ int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl
  *   g(Kw) - w = 0 with jaxopt's stopping rule (solvers.py:7-25): w0 = 0; repeat w+ = Newton(w);
  *   err = ||w+ - w||_2; until err <= tol or iters == maxiter.  Synchronises `stream` once per
  *   iteration (8-byte readback of err).  The first two Newton steps factor B = I + W^1/2 K W^1/2; later
- *   steps solve with PCG preconditioned by the last factor (refactoring if PCG stalls; set
- *   PB_LAPLACE_PCG=0 to factor every step).  Outputs: weight w (n), precision p = -h(Kw) (n),
+ *   steps solve with PCG preconditioned by the last factor when n >= "laplace_pcg_min_n" (refactoring if
+ *   PCG stalls).  Outputs: weight w (n), precision p = -h(Kw) (n),
  *   posterior mean f = K w (n); when `final_factor` != 0 the workspace additionally ends holding
  *   the Cholesky factor of B(w*) used by pb_laplace_objective / pb_predict.
  * pb_vb_fit: VBGP.weight + precision (approximators.py:332-339; VB.py:4-16).                     */

@@ -53,6 +53,7 @@ _SPEC, _LIK, _PROB = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER
 SIGNATURES = {
     "pb_version": (_i32, []),
     "pb_last_error": (C.c_char_p, []),
+    "pb_set_option": (_i32, [C.c_char_p, _f64]),
     "pb_launch_count": (C.c_longlong, []),
     "pb_profile_begin": (_i32, []),
     "pb_profile_end": (_i32, [C.POINTER(C.c_longlong), C.POINTER(_f64), C.POINTER(_f64)]),
@@ -99,6 +100,10 @@ def load():
         fn.restype, fn.argtypes = res, args
     _lib = lib
     return lib
+
+
+def set_option(name, value):
+    check(load().pb_set_option(name.encode(), float(value)))
 
 
 def check(status):

@@ -65,87 +65,154 @@ gemv_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t ld
 
 constexpr int TB = 256;        // rows/columns retired per triangular-solve step (4 leaves)
 
-// Solve the TB x TB diagonal block that starts at row/col j0 against the vector v (length nv <= TB,
-// staged in shared memory as sv) using the 64x64 leaf inverses potrf left behind:
-//   forward  (trans = false):  x_q = Dinv_q (v_q - sum_{p<q} L_qp x_p),  q = 0..3
-//   backward (trans = true):   x_q = Dinv_q^T (v_q - sum_{p>q} L_pq^T x_p),  q = 3..0
-// 256 threads: 4 threads per row of the current 64-row block.  Result left in sx (and sv is clobbered).
-__device__ void diag_block_solve(const double* __restrict__ L, int64_t ldl, const double* __restrict__ dinv, int64_t j0,
-                                 int nv, bool trans, double* sv, double* sx, double* st) {
-    const int r = threadIdx.x >> 2, q4 = threadIdx.x & 3;
-    const int nq = (nv + LEAF - 1) / LEAF;
-    for (int step = 0; step < nq; ++step) {
-        const int q = trans ? nq - 1 - step : step;
-        // t = v_q - sum_p (L_qp x_p)  |  v_q - sum_p (L_pq^T x_p)
-        double acc = 0.0;
-        if (!trans) {
-            for (int p = 0; p < q; ++p) {
-                const double* blk = L + (j0 + q * LEAF + r) * ldl + j0 + p * LEAF;     // row r of L_qp
-                if (q * LEAF + r < nv)
-                    for (int c = q4; c < LEAF; c += 4) acc = fma(blk[c], sx[p * LEAF + c], acc);
-            }
-        } else {
-            for (int p = q + 1; p < nq; ++p) {
-                // (L_pq^T x_p)[r] = sum_c L[j0 + p*64 + c][j0 + q*64 + r] x_p[c]
-                const double* blk = L + (j0 + p * LEAF) * ldl + j0 + q * LEAF + r;
-                for (int c = q4; c < LEAF; c += 4)
-                    if (p * LEAF + c < nv) acc = fma(blk[c * ldl], sx[p * LEAF + c], acc);
-            }
-        }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        if (q4 == 0) st[r] = sv[q * LEAF + r] - acc;
-        __syncthreads();
-        // x_q = Dinv_q t   |  Dinv_q^T t
-        const double* di = dinv + (j0 / LEAF + q) * LEAF * LEAF;
-        double xs = 0.0;
-        if (!trans) {
-            for (int c = q4; c <= r; c += 4) xs = fma(di[r * LEAF + c], st[c], xs);
-        } else {
-            for (int c = r + q4; c < LEAF; c += 4) xs = fma(di[c * LEAF + r], st[c], xs);
-        }
-        xs += __shfl_xor_sync(0xffffffffu, xs, 1);
-        xs += __shfl_xor_sync(0xffffffffu, xs, 2);
-        if (q4 == 0) sx[q * LEAF + r] = (q * LEAF + r < nv) ? xs : 0.0;
-        __syncthreads();
+// Inverses of the TB x TB diagonal blocks of the factor, X_j = L_jj^{-1} (row-major, lower), assembled
+// once per factorisation from the 64x64 leaf inverses:  X_qq = Dinv_q,
+// X_qp = -Dinv_q * sum_{r=p}^{q-1} L_qr X_rp  (q > p).  One CTA per diagonal block; 64^3 products on
+// register tiles (4x4 per thread) with operands staged in shared memory.  With these, every
+// triangular-solve step is a single 256x256 matvec instead of a chain of dependent 64-wide substitutions.
+constexpr int TLD = LEAF + 1;
+constexpr int TBINV_SMEM = 5 * LEAF * TLD * 8;
+
+__device__ __forceinline__ void mm64_acc(const double* A, const double* B, int ti, int tk, double (&acc)[4][4]) {
+    for (int m = 0; m < LEAF; ++m) {
+        double a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a[u] = A[(ti + 16 * u) * TLD + m];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) b[v] = B[m * TLD + tk + 16 * v];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
     }
 }
 
-// Forward substitution, one launch per TB-wide block column (look-ahead fused in):
-//   every CTA applies  b[r] -= L[r, j0:j0+TB] . x_j  to its rows (x_j was produced by the previous launch);
-//   CTA 0 owns the TB rows of the NEXT diagonal block and, once they are final, solves that block and
-//   publishes x_{j+1}, so the next launch can start immediately.  `j0 < 0` runs only the initial solve.
 __global__ void __launch_bounds__(256)
-trsv_fwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ dinv, int64_t j0,
+tb_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ dinv,
+                  double* __restrict__ tinv) {
+    extern __shared__ double tsm[];
+    double* Xc = tsm;                          // X_rp for r = p, p+1, p+2   [3][64][65]
+    double* A = tsm + 3 * LEAF * TLD;          // staged L_qr / Dinv_q        [64][65]
+    double* T = A + LEAF * TLD;                // sum_r L_qr X_rp              [64][65]
+    const int64_t j0 = (int64_t)blockIdx.x * TB;
+    const int nv = (int)(n - j0 < TB ? n - j0 : TB);
+    const int nq = (nv + LEAF - 1) / LEAF;
+    double* out = tinv + (int64_t)blockIdx.x * TB * TB;
+    const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
+    for (int e = tid; e < TB * TB; e += 256) out[e] = 0.0;
+    __syncthreads();
+    for (int p = 0; p < nq; ++p) {
+        const double* dp = dinv + (j0 / LEAF + p) * LEAF * LEAF;
+        for (int e = tid; e < LEAF * LEAF; e += 256) {
+            const int i = e >> 6, k = e & 63;
+            const double v = dp[e];
+            Xc[i * TLD + k] = v;
+            out[(p * LEAF + i) * TB + p * LEAF + k] = v;
+        }
+        __syncthreads();
+        for (int q = p + 1; q < nq; ++q) {
+            double acc[4][4] = {};
+            for (int r = p; r < q; ++r) {
+                for (int e = tid; e < LEAF * LEAF; e += 256) {
+                    const int i = e >> 6, k = e & 63;
+                    const int64_t row = j0 + q * LEAF + i;
+                    A[i * TLD + k] = (row < n) ? L[row * ldl + j0 + r * LEAF + k] : 0.0;
+                }
+                __syncthreads();
+                mm64_acc(A, Xc + (r - p) * LEAF * TLD, ti, tk, acc);
+                __syncthreads();
+            }
+            const double* dq = dinv + (j0 / LEAF + q) * LEAF * LEAF;
+            for (int e = tid; e < LEAF * LEAF; e += 256) A[(e >> 6) * TLD + (e & 63)] = dq[e];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) T[(ti + 16 * u) * TLD + tk + 16 * v] = acc[u][v];
+            __syncthreads();
+            double x[4][4] = {};
+            mm64_acc(A, T, ti, tk, x);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int i = ti + 16 * u, k = tk + 16 * v;
+                    out[(q * LEAF + i) * TB + p * LEAF + k] = -x[u][v];
+                    if (q - p <= 2) Xc[(q - p) * LEAF * TLD + i * TLD + k] = -x[u][v];
+                }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int TSV_THREADS = 1024;     // 32 warps per CTA in the triangular-solve step kernels
+
+// x = X v (forward, X = L_jj^{-1}, lower, row-major) for one TB-block: one warp per row (coalesced row
+// reads + shuffle reduction), 8 rows per warp.  v staged in shared memory (sv), result to sx.
+__device__ __forceinline__ void tinv_matvec_fwd(const double* __restrict__ X, const double* sv, double* sx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < TB / 32; ++u) {
+        const int r = warp + 32 * u;
+        const double* row = X + (int64_t)r * TB;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < TB / 32; ++k) {
+            const int c = lane + 32 * k;
+            if (c <= r) acc = fma(row[c], sv[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sx[r] = acc;
+    }
+    __syncthreads();
+}
+
+// x = X^T v (backward): thread (col = t % 256, group = t / 256) sums rows r = col + group, step 4
+// (coalesced across the 256 columns for every r); the four partials meet in shared memory.
+__device__ __forceinline__ void tinv_matvec_bwd(const double* __restrict__ X, const double* sv, double* sx, double* red) {
+    const int col = threadIdx.x & (TB - 1), grp = threadIdx.x >> 8;
+    double acc = 0.0;
+    for (int r = col + grp; r < TB; r += 4) acc = fma(X[(int64_t)r * TB + col], sv[r], acc);
+    red[grp * TB + col] = acc;
+    __syncthreads();
+    if (grp == 0) sx[col] = (red[col] + red[TB + col]) + (red[2 * TB + col] + red[3 * TB + col]);
+    __syncthreads();
+}
+
+// Forward substitution, one launch per TB-wide block column (look-ahead fused in):
+//   every CTA applies  b[r] -= L[r, j0:j0+TB] . x_j  to its 256 rows, 8 per warp (x_j was produced by the
+//   previous launch);  CTA 0 owns the rows of the NEXT diagonal block and, once they are final, multiplies
+//   them by that block's inverse and publishes x_{j+1}, so the next launch can start immediately.
+//   `j0 < 0` runs only the initial solve.
+__global__ void __launch_bounds__(TSV_THREADS)
+trsv_fwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ tinv, int64_t j0,
                 double* __restrict__ b, double* __restrict__ x) {
-    __shared__ double sx[TB], sv[TB], st[LEAF];
+    __shared__ double sx[TB], sv[TB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (j0 < 0) {                                   // bootstrap: x_0 = L_00^{-1} b_0
         const int nv = (int)(n < TB ? n : TB);
-        sv[threadIdx.x] = threadIdx.x < nv ? b[threadIdx.x] : 0.0;
+        if (threadIdx.x < TB) sv[threadIdx.x] = threadIdx.x < nv ? b[threadIdx.x] : 0.0;
         __syncthreads();
-        diag_block_solve(L, ldl, dinv, 0, nv, false, sv, sx, st);
+        tinv_matvec_fwd(tinv, sv, sx);
         if (threadIdx.x < nv) x[threadIdx.x] = sx[threadIdx.x];
         return;
     }
-    sx[threadIdx.x] = x[j0 + threadIdx.x];          // block j is full width whenever rows remain below it
+    if (threadIdx.x < TB) sx[threadIdx.x] = x[j0 + threadIdx.x];     // block j is full width whenever rows remain below it
     __syncthreads();
     const int64_t next0 = j0 + TB;
-    // CTA 0: the TB rows of the next diagonal block (32 per warp); CTA c >= 1: 64 rows (8 per warp)
-    const int64_t row_begin = blockIdx.x == 0 ? next0 : next0 + TB + (int64_t)(blockIdx.x - 1) * 64;
-    const int rows_here = blockIdx.x == 0 ? TB : 64;
-    const int per_warp = rows_here / 8;
+    const int64_t row_begin = next0 + (int64_t)blockIdx.x * TB + warp * 8;
     double xr[8];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         xr[2 * k] = sx[2 * lane + 64 * k];
         xr[2 * k + 1] = sx[2 * lane + 64 * k + 1];
     }
-    for (int rr = 0; rr < per_warp; rr += 4) {
+#pragma unroll
+    for (int rr = 0; rr < 8; rr += 4) {
         double acc[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int64_t r = row_begin + warp * per_warp + rr + u;
+            const int64_t r = row_begin + rr + u;
             acc[u] = 0.0;
             if (r < n) {
                 const double2* lp = reinterpret_cast<const double2*>(L + r * ldl + j0) + lane;
@@ -160,44 +227,43 @@ trsv_fwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const doub
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const double sum = warp_sum(acc[u]);
-            const int64_t r = row_begin + warp * per_warp + rr + u;
+            const int64_t r = row_begin + rr + u;
             if (lane == 0 && r < n) b[r] -= sum;
         }
     }
     if (blockIdx.x != 0 || next0 >= n) return;
-    __threadfence_block();
-    __syncthreads();
+    __syncthreads();                                 // CTA 0: its 256 rows (the next diagonal block) are final
     const int nv = (int)(n - next0 < TB ? n - next0 : TB);
-    sv[threadIdx.x] = threadIdx.x < nv ? b[next0 + threadIdx.x] : 0.0;
+    if (threadIdx.x < TB) sv[threadIdx.x] = threadIdx.x < nv ? b[next0 + threadIdx.x] : 0.0;
     __syncthreads();
-    diag_block_solve(L, ldl, dinv, next0, nv, false, sv, sx, st);
+    tinv_matvec_fwd(tinv + (next0 / TB) * TB * TB, sv, sx);
     if (threadIdx.x < nv) x[next0 + threadIdx.x] = sx[threadIdx.x];
 }
 
 // Backward substitution L^T x = y, blocks from the bottom up, same one-launch-per-step scheme:
 //   every CTA applies  y[c] -= sum_{r in block j} L[j0 + r][c] x_j[r]  to its 256 columns c < j0
-//   (two 128-row halves per CTA, 16-byte coalesced row reads);
-//   the LAST CTA owns the columns of the next (upper) diagonal block, solves it and publishes x_{j-1}.
-__global__ void __launch_bounds__(256)
-trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ dinv, int64_t j0,
+//   (eight 32-row groups per CTA, 16-byte coalesced row reads, partials combined in shared memory);
+//   the LAST CTA owns the columns of the next (upper) diagonal block and publishes x_{j-1}.
+__global__ void __launch_bounds__(TSV_THREADS)
+trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ tinv, int64_t j0,
                 int bootstrap, double* __restrict__ y, double* __restrict__ x) {
-    __shared__ double sx[TB], sv[TB], st[LEAF];
-    __shared__ double2 part[128];
+    __shared__ double sx[TB], sv[TB];
+    __shared__ double red[8 * TB];
     const int nvj = (int)(n - j0 < TB ? n - j0 : TB);
     if (bootstrap) {                                // x_last = L_last^{-T} y_last
-        sv[threadIdx.x] = threadIdx.x < nvj ? y[j0 + threadIdx.x] : 0.0;
+        if (threadIdx.x < TB) sv[threadIdx.x] = threadIdx.x < nvj ? y[j0 + threadIdx.x] : 0.0;
         __syncthreads();
-        diag_block_solve(L, ldl, dinv, j0, nvj, true, sv, sx, st);
+        tinv_matvec_bwd(tinv + (j0 / TB) * TB * TB, sv, sx, red);
         if (threadIdx.x < nvj) x[j0 + threadIdx.x] = sx[threadIdx.x];
         return;
     }
-    sx[threadIdx.x] = threadIdx.x < nvj ? x[j0 + threadIdx.x] : 0.0;
+    if (threadIdx.x < TB) sx[threadIdx.x] = threadIdx.x < nvj ? x[j0 + threadIdx.x] : 0.0;
     __syncthreads();
-    const int half = threadIdx.x >> 7, cp = threadIdx.x & 127;
-    const int64_t c = (int64_t)blockIdx.x * 256 + 2 * cp;          // this thread's column pair (c, c+1) < j0
+    const int grp = threadIdx.x >> 7, cp = threadIdx.x & 127;       // 8 row groups x 128 column pairs
+    const int64_t c = (int64_t)blockIdx.x * TB + 2 * cp;            // columns (c, c+1) < j0
     double2 acc = make_double2(0.0, 0.0);
-    if (c < j0) {
-        const int r_lo = half * 128, r_hi = min(nvj, r_lo + 128);
+    {
+        const int r_lo = grp * 32, r_hi = min(nvj, r_lo + 32);
         const double* lp = L + (j0 + r_lo) * ldl + c;
 #pragma unroll 8
         for (int r = r_lo; r < r_hi; ++r) {
@@ -207,24 +273,22 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const doub
             lp += ldl;
         }
     }
-    if (half == 1) part[cp] = acc;
+    red[grp * TB + 2 * cp] = acc.x;
+    red[grp * TB + 2 * cp + 1] = acc.y;
     __syncthreads();
-    if (half == 0 && c < j0) {
-        const double2 o = part[cp];
-        double2* yp = reinterpret_cast<double2*>(y + c);
-        double2 cur = *yp;
-        cur.x -= acc.x + o.x;
-        cur.y -= acc.y + o.y;
-        *yp = cur;
+    if (threadIdx.x < TB) {
+        double ssum = 0.0;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) ssum += red[g * TB + threadIdx.x];
+        y[(int64_t)blockIdx.x * TB + threadIdx.x] -= ssum;
     }
     if (blockIdx.x != gridDim.x - 1) return;
-    __threadfence_block();
     __syncthreads();
     const int64_t p0 = j0 - TB;                      // previous (upper) block, always full width
-    sv[threadIdx.x] = y[p0 + threadIdx.x];
+    if (threadIdx.x < TB) sv[threadIdx.x] = y[p0 + threadIdx.x];
     __syncthreads();
-    diag_block_solve(L, ldl, dinv, p0, TB, true, sv, sx, st);
-    x[p0 + threadIdx.x] = sx[threadIdx.x];
+    tinv_matvec_bwd(tinv + (p0 / TB) * TB * TB, sv, sx, red);
+    if (threadIdx.x < TB) x[p0 + threadIdx.x] = sx[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(1024)
@@ -252,22 +316,36 @@ int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const dou
     PB_CHECK((ldl & 1) == 0 && (reinterpret_cast<uintptr_t>(L) & 15) == 0, PB_ERR_INVALID,
              "trsv: factor must be 16-byte aligned with an even leading dimension");
     const int64_t nblk = ceil_div<int64_t>(n, TB);
+    const double* tinv = dinv + ceil_div<int64_t>(n, LEAF) * LEAF * LEAF;     // TB-block inverses follow the leaf inverses
     if (!trans) {
-        trsv_fwd_kernel<<<1, 256, 0, stream>>>(L, n, ldl, dinv, -1, rhs, x); pb::note_launch();
+        trsv_fwd_kernel<<<1, TSV_THREADS, 0, stream>>>(L, n, ldl, tinv, -1, rhs, x); pb::note_launch();
         for (int64_t jb = 0; jb + 1 < nblk; ++jb) {
             const int64_t j0 = jb * TB;
-            const int64_t below_next = n - j0 - 2 * TB;      // rows below the next diagonal block
-            const unsigned grid = 1u + (below_next > 0 ? (unsigned)ceil_div<int64_t>(below_next, 64) : 0u);
-            trsv_fwd_kernel<<<grid, 256, 0, stream>>>(L, n, ldl, dinv, j0, rhs, x); pb::note_launch();
+            const unsigned grid = (unsigned)ceil_div<int64_t>(n - j0 - TB, TB);      // 256 rows per CTA below block j
+            trsv_fwd_kernel<<<grid, TSV_THREADS, 0, stream>>>(L, n, ldl, tinv, j0, rhs, x); pb::note_launch();
         }
     } else {
         const int64_t jlast = (nblk - 1) * TB;
-        trsv_bwd_kernel<<<1, 256, 0, stream>>>(L, n, ldl, dinv, jlast, 1, rhs, x); pb::note_launch();
+        trsv_bwd_kernel<<<1, TSV_THREADS, 0, stream>>>(L, n, ldl, tinv, jlast, 1, rhs, x); pb::note_launch();
         for (int64_t jb = nblk - 1; jb >= 1; --jb) {
             const int64_t j0 = jb * TB;
-            trsv_bwd_kernel<<<(unsigned)(j0 / 256), 256, 0, stream>>>(L, n, ldl, dinv, j0, 0, rhs, x); pb::note_launch();
+            trsv_bwd_kernel<<<(unsigned)(j0 / TB), TSV_THREADS, 0, stream>>>(L, n, ldl, tinv, j0, 0, rhs, x); pb::note_launch();
         }
     }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// Builds the TB-block inverses behind the leaf inverses in the potrf workspace (called at the end of potrf).
+int build_block_inverses(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* dinv) {
+    if (n == 0) return PB_OK;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(tb_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBINV_SMEM));
+        configured = true;
+    }
+    double* tinv = dinv + ceil_div<int64_t>(n, LEAF) * LEAF * LEAF;
+    tb_inverse_kernel<<<(unsigned)ceil_div<int64_t>(n, TB), 256, TBINV_SMEM, stream>>>(L, n, ldl, dinv, tinv); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -19,6 +19,11 @@ void note_launch();
 bool profiling_enabled();
 void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops);
 
+// tunables set through pb_set_option (capi.cu)
+long long opt_pcg_min_n();
+int opt_potrf_nb();
+bool opt_lookahead();
+
 #define PB_CUDA(expr)                                                                         \
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
@@ -109,6 +114,7 @@ int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64
 int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const double* dinv, bool trans, double* rhs,
          double* x);
 int logdet_chol(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* out);
+int build_block_inverses(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* dinv);
 
 // likelihood.cu
 int likelihood(cudaStream_t stream, const pb_likelihood_spec& spec, const double* f, const void* y, int64_t n,

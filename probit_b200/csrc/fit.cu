@@ -396,14 +396,7 @@ int pcg_solve(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const d
     return PB_OK;
 }
 
-bool pcg_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PB_LAPLACE_PCG");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
+bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
 
 }  // namespace
 }  // namespace pb
@@ -464,7 +457,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         // reuse the last factor as a PCG preconditioner and refactor only if PCG stalls.
         const double* xsol = ws.vec(V_C);
         bool solved = false;
-        if (have_factor && it >= 2 && pcg_enabled()) {
+        if (have_factor && it >= 2 && pcg_enabled(n)) {
             int used = -1;
             PB_TRY(pcg_solve(st, ws, n, ws.vec(V_S), ws.vec(V_C), 60, 1e-13, &used));
             if (used >= 0) {

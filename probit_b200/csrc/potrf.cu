@@ -172,11 +172,7 @@ int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
 }  // namespace
 
 int potrf_block_size(int64_t n) {
-    static int forced = -1;
-    if (forced < 0) {
-        const char* e = getenv("PB_POTRF_NB");
-        forced = e ? atoi(e) : 0;
-    }
+    const int forced = opt_potrf_nb();
     if (forced > 0) return forced / 64 * 64 > 0 ? forced / 64 * 64 : 64;
     if (n <= 2048) return 256;
     return 512;
@@ -211,14 +207,7 @@ struct EventPool {
     }
 };
 
-bool lookahead_enabled() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("PB_POTRF_LOOKAHEAD");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v == 1;
-}
+bool lookahead_enabled() { return opt_lookahead(); }
 
 }  // namespace
 
@@ -247,7 +236,7 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
                 PB_TRY(gemm_nt(stream, m, m, nb, -1.0, P, lda, P, lda, 1.0, P + nb, lda, true));
             }
         }
-        return PB_OK;
+        return build_block_inverses(stream, A, n, lda, cm.dinv);
     }
 
     cudaStream_t side;
@@ -296,7 +285,7 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
         ev_panel = ev_next;
     }
     PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
-    return PB_OK;
+    return build_block_inverses(stream, A, n, lda, cm.dinv);
 }
 
 int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
@@ -308,8 +297,10 @@ int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, 
 }  // namespace pb
 
 extern "C" int64_t pb_potrf_workspace_bytes(int64_t n) {
+    // [ceil(n/64) leaf inverses, 64x64] followed by [ceil(n/256) diagonal-block inverses, 256x256] (blas2.cu)
     const int64_t leaves = (n + pb::LEAF - 1) / pb::LEAF;
-    return (leaves > 0 ? leaves : 1) * pb::LEAF * pb::LEAF * (int64_t)sizeof(double);
+    const int64_t blocks = (n + 255) / 256;
+    return ((leaves > 0 ? leaves : 1) * pb::LEAF * pb::LEAF + (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
 }
 
 extern "C" int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,

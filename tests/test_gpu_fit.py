@@ -139,3 +139,24 @@ def test_full_size_properties_n65536():
     assert 0.0 < ld < n * 0.5 * np.log(2.0 + 1.0) * 10
     del K, A, fac
     torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("pcg_min_n", [0, 1 << 40])
+def test_newton_policies_agree(pcg_min_n):
+    """Stale-factor PCG Newton steps (forced on at small N) and factor-every-step give the oracle's iterates."""
+    from probit_b200 import _lib
+    X, y, params, family = ordinal_problem(11, 800, 4, 5, "matern12")
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)
+    _lib.set_option("laplace_pcg_min_n", pcg_min_n)
+    try:
+        w, prec = p.approximate_posterior(params)
+        res = p.last_result
+    finally:
+        _lib.set_option("laplace_pcg_min_n", 24576)
+    assert res.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+    if pcg_min_n == 0:
+        assert res.factorizations == 2 and res.pcg_iterations > 0
+    else:
+        assert res.factorizations == res.iterations and res.pcg_iterations == 0

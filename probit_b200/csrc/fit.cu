@@ -453,13 +453,13 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
         PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));       // K b
         mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C)); pb::note_launch();
-        // x = B^{-1} (s o K b).  The first two iterations factor B (W moves a lot from f = 0); later ones
-        // reuse the last factor as a PCG preconditioner and refactor only if PCG stalls.
+        // x = B^{-1} (s o K b).  The first iteration factors B; later ones reuse the last factor as a PCG
+        // preconditioner (rescaled by s_fac/s) and refactor only if PCG stalls.
         const double* xsol = ws.vec(V_C);
         bool solved = false;
-        if (have_factor && it >= 2 && pcg_enabled(n)) {
+        if (have_factor && it >= 1 && pcg_enabled(n)) {
             int used = -1;
-            PB_TRY(pcg_solve(st, ws, n, ws.vec(V_S), ws.vec(V_C), 60, 1e-13, &used));
+            PB_TRY(pcg_solve(st, ws, n, ws.vec(V_S), ws.vec(V_C), 48, 1e-13, &used));
             if (used >= 0) {
                 solved = true;
                 xsol = ws.vec(V_Y);

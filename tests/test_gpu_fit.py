@@ -157,6 +157,6 @@ def test_newton_policies_agree(pcg_min_n):
     assert res.iterations == len(o.trace)
     assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
     if pcg_min_n == 0:
-        assert res.factorizations == 2 and res.pcg_iterations > 0
+        assert res.factorizations <= 2 and res.pcg_iterations > 0
     else:
         assert res.factorizations == res.iterations and res.pcg_iterations == 0

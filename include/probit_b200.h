@@ -125,6 +125,17 @@ int64_t pb_potrf_workspace_bytes(int64_t n);
 int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,
              int64_t workspace_bytes, int32_t* info);
 
+/* Fill the solve workspace (64x64 leaf inverses + 256x256 diagonal-block inverses used by pb_trsv /
+ * pb_trsm_right_lt) for a factor L that was produced elsewhere (multi-GPU block-cyclic Cholesky). */
+int pb_rebuild_solve_workspace(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, void* workspace,
+                               int64_t workspace_bytes);
+
+/* out[r][c] = s_i K_ij s_j (+ a + s_i^2 jitter where i == j), i = row0 + r, j = col0 + c: one rectangular
+ * block of a I + s s^T o (K + jitter I) (s may be NULL = ones), e.g. a block column of a block-cyclic layout. */
+int pb_transform_block(pb_stream_t stream, const double* K, int64_t ldk, const double* s, double a,
+                       double jitter, int64_t row0, int64_t col0, int64_t rows, int64_t cols, double* out,
+                       int64_t ldo);
+
 /* C[M x N] = alpha * A[M x K] * B[N x K]^T + beta * C (all row-major). Exposed for tests/bench. */
 int pb_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
                int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
@@ -181,6 +192,15 @@ typedef struct pb_problem {
 /* Workspace layout is private; size it with pb_fit_workspace_bytes(n, D).  It holds K (n x ld),
  * the factor buffer (n x ld), features and O(n) vectors. */
 int64_t pb_fit_workspace_bytes(int64_t n, int D);
+/* External factorisation hook (SURVEY.md §8e "large-N Cholesky"): when set, every factorisation inside the
+ * fit / predict drivers — a I + s s^T o (K + jitter I) -> lower factor in `L` plus the solve workspace —
+ * is delegated to `fn` (the multi-GPU block-cyclic Cholesky of probit_b200/distributed.py, which broadcasts
+ * panels with NCCL).  The callback must leave the factor in the lower triangle of L, fill
+ * `potrf_workspace` (pb_rebuild_solve_workspace) and set *info_dev.  NULL restores the single-GPU path. */
+typedef int (*pb_factor_fn)(void* user, pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* s,
+                            double a, double jitter, double* L, int64_t ldl, void* potrf_workspace,
+                            int64_t potrf_workspace_bytes, int32_t* info_dev);
+int pb_set_factor_callback(pb_factor_fn fn, void* user);
 /* Build features + K(theta) into the workspace (what every fit does first); and locate K inside it. */
 int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
 int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk);

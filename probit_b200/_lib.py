@@ -47,6 +47,8 @@ class NumericError(ProbitB200Error):
 
 
 _p, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+FACTOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
+                        C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p)
 _SPEC, _LIK, _PROB = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER(Problem)
 
 # name -> (restype, argtypes); mirrors include/probit_b200.h one to one
@@ -67,6 +69,9 @@ SIGNATURES = {
     "pb_copy_lower_add_diag": (_i32, [_p, _p, _i64, _i64, _f64, _p, _i64]),
     "pb_potrf_workspace_bytes": (_i64, [_i64]),
     "pb_potrf": (_i32, [_p, _p, _i64, _i64, _p, _i64, _p]),
+    "pb_rebuild_solve_workspace": (_i32, [_p, _p, _i64, _i64, _p, _i64]),
+    "pb_transform_block": (_i32, [_p, _p, _i64, _p, _f64, _f64, _i64, _i64, _i64, _i64, _p, _i64]),
+    "pb_set_factor_callback": (_i32, [_p, _p]),
     "pb_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _f64, _p, _i64, _i32]),
     "pb_symv": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "pb_trsv": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _p]),

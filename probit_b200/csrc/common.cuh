@@ -106,6 +106,8 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
              double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
 int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale);
+int transform_block(cudaStream_t stream, const double* K, int64_t ldk, const double* s, double a, double jitter,
+                    int64_t row0, int64_t col0, int64_t rows, int64_t cols, double* out, int64_t ldo);
 int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, const double* s, double a,
                   double jitter, double* B, int64_t ldb);
 

@@ -14,6 +14,7 @@
 // (tests/test_oracle_fit.py) and the iteration count is identical.
 #include "likelihood.cuh"
 #include <cstdlib>
+#include <mutex>
 
 namespace pb {
 
@@ -341,10 +342,33 @@ int posterior_stats(cudaStream_t st, const pb_problem* prob, const lik::Params& 
     return finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_FTW);
 }
 
+// Optional external factorisation (multi-GPU block-cyclic Cholesky, probit_b200/distributed.py).
+std::mutex g_factor_mu;
+pb_factor_fn g_factor_fn = nullptr;
+void* g_factor_user = nullptr;
+
+// Factor a I + s s^T o (K + jitter I) into ws.B() (lower) and fill the solve workspace.
+int factor_matrix(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double a, double jitter) {
+    pb_factor_fn fn;
+    void* user;
+    {
+        std::lock_guard<std::mutex> lock(g_factor_mu);
+        fn = g_factor_fn;
+        user = g_factor_user;
+    }
+    if (fn) {
+        const int status = fn(user, reinterpret_cast<pb_stream_t>(st), ws.K(), n, ws.L.ld, s, a, jitter, ws.B(), ws.L.ld,
+                              ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info());
+        PB_CHECK(status == PB_OK, status, "external factorisation callback failed with %d", status);
+        return PB_OK;
+    }
+    PB_TRY(sym_transform(st, ws.K(), n, ws.L.ld, s, a, jitter, ws.B(), ws.L.ld));
+    return potrf(st, ws.B(), n, ws.L.ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info());
+}
+
 // B = I + s s^T o (K + jitter I), factor in place, logdet -> device scalar
 int factor_B(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double jitter) {
-    PB_TRY(sym_transform(st, ws.K(), n, ws.L.ld, s, 1.0, jitter, ws.B(), ws.L.ld));
-    PB_TRY(potrf(st, ws.B(), n, ws.L.ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info()));
+    PB_TRY(factor_matrix(st, ws, n, s, 1.0, jitter));
     return logdet_chol(st, ws.B(), n, ws.L.ld, ws.scalars() + S_LOGDET);
 }
 
@@ -404,6 +428,13 @@ bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
 using namespace pb;
 
 extern "C" int64_t pb_fit_workspace_bytes(int64_t n, int D) { return make_layout(n, D).total; }
+
+extern "C" int pb_set_factor_callback(pb_factor_fn fn, void* user) {
+    std::lock_guard<std::mutex> lock(g_factor_mu);
+    g_factor_fn = fn;
+    g_factor_user = user;
+    return PB_OK;
+}
 
 extern "C" int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes) {
     Ws ws;
@@ -543,8 +574,7 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
     PB_TRY(build_gram(st, prob, ws));
     PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
     // L = chol(sigma^2 I + K) (VB.py:10) — loop invariant, factored once (no jitter: raw-array path)
-    PB_TRY(sym_transform(st, ws.K(), n, ld, nullptr, sigma * sigma, 0.0, ws.B(), ld));
-    PB_TRY(potrf(st, ws.B(), n, ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info()));
+    PB_TRY(factor_matrix(st, ws, n, nullptr, sigma * sigma, 0.0));
     PB_TRY(logdet_chol(st, ws.B(), n, ld, ws.scalars() + S_LOGDET));
     PB_CUDA(cudaMemsetAsync(ws.vec(V_W), 0, n * sizeof(double), st));
     result_host->factorizations = 1;

@@ -243,6 +243,25 @@ sym_transform_kernel(const double* __restrict__ K, int64_t n, int64_t ldk, const
     }
 }
 
+// out[r][c] = s_i K_ij s_j (+ a + s_i^2 jitter on the global diagonal) for the rectangle
+// i = row0 + r, j = col0 + c — the block-cyclic layouts of the multi-GPU Cholesky take their block columns
+// of B = a I + s s^T o (K + jitter I) straight from the resident K with this.
+__global__ void __launch_bounds__(256)
+transform_block_kernel(const double* __restrict__ K, int64_t ldk, const double* __restrict__ s, double a,
+                       double jitter, int64_t row0, int64_t col0, int64_t rows, int64_t cols,
+                       double* __restrict__ out, int64_t ldo) {
+    const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (c >= cols) return;
+    const double sj = s ? s[col0 + c] : 1.0;
+    for (int64_t r = (int64_t)blockIdx.y * 64; r < rows && r < (int64_t)(blockIdx.y + 1) * 64; ++r) {
+        const int64_t i = row0 + r, j = col0 + c;
+        const double si = s ? s[i] : 1.0;
+        double v = K[i * ldk + j];
+        v = (i == j) ? a + si * (v + jitter) * sj : si * v * sj;
+        out[r * ldo + c] = v;
+    }
+}
+
 inline int64_t tri_tiles(int64_t n) {
     const int64_t T = ceil_div<int64_t>(n, TILE);
     return T * (T + 1) / 2;
@@ -322,7 +341,24 @@ int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, 
     return PB_OK;
 }
 
+int transform_block(cudaStream_t stream, const double* K, int64_t ldk, const double* s, double a, double jitter,
+                    int64_t row0, int64_t col0, int64_t rows, int64_t cols, double* out, int64_t ldo) {
+    if (rows <= 0 || cols <= 0) return PB_OK;
+    dim3 grid((unsigned)ceil_div<int64_t>(cols, 256), (unsigned)ceil_div<int64_t>(rows, 64));
+    PB_CHECK(grid.y < 65536, PB_ERR_INVALID, "transform_block: too many rows");
+    transform_block_kernel<<<grid, 256, 0, stream>>>(K, ldk, s, a, jitter, row0, col0, rows, cols, out, ldo); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 }  // namespace pb
+
+extern "C" int pb_transform_block(pb_stream_t stream, const double* K, int64_t ldk, const double* s, double a,
+                                  double jitter, int64_t row0, int64_t col0, int64_t rows, int64_t cols, double* out,
+                                  int64_t ldo) {
+    return pb::transform_block(reinterpret_cast<cudaStream_t>(stream), K, ldk, s, a, jitter, row0, col0, rows, cols,
+                               out, ldo);
+}
 
 extern "C" int pb_feature_dim(const pb_kernel_spec* spec, int D) { return pb::feature_dim(*spec, D); }
 

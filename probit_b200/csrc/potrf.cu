@@ -127,6 +127,46 @@ potrf_leaf_kernel(double* __restrict__ A, int64_t lda, int nv, double* __restric
 
 constexpr int LEAF_SMEM = (2 * LEAF * LDS + 3 * LEAF) * 8;
 
+// Inverse of every 64x64 diagonal leaf of an ALREADY factored matrix (one CTA per leaf): the same row-by-row
+// substitution as in potrf_leaf_kernel.  Used when the factor was produced elsewhere (multi-GPU Cholesky).
+__global__ void __launch_bounds__(256, 1)
+leaf_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __restrict__ dinv) {
+    extern __shared__ double leaf_smem[];
+    double* Ls = leaf_smem;
+    double* Vs = Ls + LEAF * LDS;
+    double* rdiag = Vs + LEAF * LDS;
+    const int tid = threadIdx.x;
+    const int64_t j0 = (int64_t)blockIdx.x * LEAF;
+    const int nv = (int)(n - j0 < LEAF ? n - j0 : LEAF);
+    for (int e = tid; e < LEAF * LEAF; e += 256) {
+        const int i = e >> 6, k = e & 63;
+        double v = (i == k) ? 1.0 : 0.0;
+        if (i < nv && k <= i) v = L[(j0 + i) * ldl + j0 + k];
+        else if (k > i) v = 0.0;
+        Ls[i * LDS + k] = v;
+    }
+    __syncthreads();
+    if (tid < LEAF) rdiag[tid] = 1.0 / Ls[tid * LDS + tid];
+    __syncthreads();
+    {
+        const int c = tid >> 2, q = tid & 3;
+        for (int i = 0; i < LEAF; ++i) {
+            double s = 0.0;
+            for (int k = c + q; k < i; k += 4) s = fma(Ls[i * LDS + k], Vs[k * LDS + c], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0) Vs[i * LDS + c] = (i < c) ? 0.0 : ((i == c ? 1.0 : 0.0) - s) * rdiag[i];
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* out = dinv + (int64_t)blockIdx.x * LEAF * LEAF;
+    for (int e = tid; e < LEAF * LEAF; e += 256) {
+        const int i = e >> 6, k = e & 63;
+        out[e] = (k <= i) ? Vs[i * LDS + k] : 0.0;
+    }
+}
+
 struct Ctx {
     cudaStream_t stream;
     int64_t lda;
@@ -288,6 +328,21 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
     return build_block_inverses(stream, A, n, lda, cm.dinv);
 }
 
+int rebuild_solve_workspace(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, void* workspace,
+                            int64_t workspace_bytes) {
+    PB_CHECK(workspace_bytes >= pb_potrf_workspace_bytes(n), PB_ERR_INVALID, "rebuild_solve_workspace: workspace too small");
+    if (n == 0) return PB_OK;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(leaf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
+        configured = true;
+    }
+    double* dinv = reinterpret_cast<double*>(workspace);
+    leaf_inverse_kernel<<<(unsigned)((n + LEAF - 1) / LEAF), 256, LEAF_SMEM, stream>>>(L, n, ldl, dinv); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return build_block_inverses(stream, L, n, ldl, dinv);
+}
+
 int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
                   double* X, int64_t m, int64_t ldx) {
     Ctx c{stream, ldl, const_cast<double*>(reinterpret_cast<const double*>(potrf_workspace)), nullptr};
@@ -306,6 +361,11 @@ extern "C" int64_t pb_potrf_workspace_bytes(int64_t n) {
 extern "C" int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,
                         int64_t workspace_bytes, int32_t* info) {
     return pb::potrf(reinterpret_cast<cudaStream_t>(stream), A, n, lda, workspace, workspace_bytes, info);
+}
+
+extern "C" int pb_rebuild_solve_workspace(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, void* workspace,
+                                          int64_t workspace_bytes) {
+    return pb::rebuild_solve_workspace(reinterpret_cast<cudaStream_t>(stream), L, n, ldl, workspace, workspace_bytes);
 }
 
 extern "C" int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl,

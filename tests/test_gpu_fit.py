@@ -160,3 +160,25 @@ def test_newton_policies_agree(pcg_min_n):
         assert res.factorizations <= 2 and res.pcg_iterations > 0
     else:
         assert res.factorizations == res.iterations and res.pcg_iterations == 0
+
+
+def test_block_cyclic_factorization_hook_single_gpu():
+    """The multi-GPU Cholesky path (factor callback -> block-cyclic panels -> rebuilt solve workspace) with a
+    world of one: same results as the oracle for fit, predict and objective."""
+    from probit_b200.distributed import DistributedFactorization
+    X, y, params, family = ordinal_problem(21, 700, 4, 5, "matern12")
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)
+    Xs = np.random.default_rng(2).uniform(-0.5, 1.5, size=(90, 4))
+    m_ref, v_ref = o.predict(Xs, params, w_ref, p_ref)
+    with DistributedFactorization(p, nb=128) as hook:
+        w, prec = p.approximate_posterior(params)
+        m, v = p.predict(Xs, params, w, prec)
+        obj = p.objective()(params)
+        assert hook.error is None and hook.calls >= 3
+    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+    assert relerr(m.cpu().numpy(), m_ref) < TOL and relerr(v.cpu().numpy(), v_ref) < TOL
+    assert abs(obj - o.objective()(params)) < TOL * abs(obj)
+    # and the hook is gone afterwards
+    w2, _ = p.approximate_posterior(params)
+    assert relerr(w2.cpu().numpy(), w_ref) < TOL

@@ -211,6 +211,19 @@ int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int3
               void* workspace, int64_t workspace_bytes, double* weight, double* precision,
               double* posterior_mean, pb_fit_result* result_host);
 
+/* ---- A11: evidence gradient ("next" row 1) ------------------------------------------------------
+ * d objective_LA / d (kernel scale, kernel stretch_out, noise std) at the converged weight: the closed form
+ * (Rasmussen & Williams Alg. 5.1 / §5.5.1) of what JAX's reverse pass through fixed_point_layer returns
+ * (probit/implicit/solvers.py:28-64, probit/approximators.py:132-134).  Call right after
+ * pb_laplace_fit(final_factor = 1): the workspace must hold K and the factor of B(w*); the factor is
+ * consumed.  grad_host[0..2] = d/dscale, d/dstretch_out, d/dsigma (NaN unless the likelihood is Gaussian;
+ * ordinal sigma / cutpoint derivatives are not implemented — the reference's examples keep them fixed).
+ * Cost: one N x N triangular inverse + U U^T (both DMMA GEMMs) + two passes over K.                  */
+int64_t pb_gradient_scratch_bytes(int64_t n);
+int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
+                        const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
+                        double* grad_host);
+
 /* ---- A10: predict -----------------------------------------------------------------------------
  * Approximator.predict (approximators.py:154-180): mean = K_*f w,
  * var = k_** - diag(K_*f (K + P^-1)^-1 K_f*) = k_** - || L_B^-1 (s o k_*) ||^2, s = sqrt(P).

@@ -170,6 +170,10 @@ class Approximator(ABC):
         w, p, _ = self._fit(parameters, final_factor=False)
         return w, p
 
+    def value_and_grad(self):
+        """approximators.py:132-134: callable(parameters) -> (objective, gradient with the structure of `parameters`)."""
+        raise NotImplementedError(f"{self!r}: value_and_grad is implemented for LaplaceGP only")
+
 
 class LaplaceGP(Approximator):
     """probit/approximators.py:213-277 + probit/implicit/Laplace.py."""
@@ -222,6 +226,71 @@ class LaplaceGP(Approximator):
             r = self.last_result
             return -r.sum_ll + 0.5 * r.ftw + r.logdet
         return obj
+
+
+def _flatten_scalars(tree):
+    """Flatten a scalar / nested tuple of scalars; returns (list_of_floats, rebuild(list) -> same structure)."""
+    if isinstance(tree, (tuple, list)):
+        parts = [_flatten_scalars(t) for t in tree]
+        sizes = [len(p[0]) for p in parts]
+        flat = [x for p in parts for x in p[0]]
+
+        def rebuild(vals):
+            out, i = [], 0
+            for (_, rb), k in zip(parts, sizes):
+                out.append(rb(vals[i:i + k]))
+                i += k
+            return type(tree)(out) if isinstance(tree, tuple) else out
+        return flat, rebuild
+    return [float(tree)], (lambda vals: vals[0])
+
+
+def _laplace_value_and_grad(self):
+    """LaplaceGP.value_and_grad(): negative Laplace evidence and its gradient.
+
+    Replaces jit(value_and_grad(objective)) (approximators.py:132-134), i.e. JAX's reverse pass through
+    `fixed_point_layer` (implicit/solvers.py:28-64), by the closed form evaluated on the GPU
+    (pb_laplace_gradient).  The gradient w.r.t. the kernel's scale and stretch is mapped back to the user's
+    `prior_parameters` through the Jacobian of the (host-side, cheap) kernel-spec lowering, taken by central
+    differences.  Returned structure mirrors `parameters`; entries without an implemented derivative
+    (ordinal noise std and cutpoints — constants in examples/classification.py:416-417) are None."""
+    def vg(parameters):
+        prior_parameters, likelihood_parameters = parameters
+        w, p, _ = self._fit(parameters, final_factor=True)
+        r = self.last_result
+        value = -r.sum_ll + 0.5 * r.ftw + r.logdet
+        prob, keep = self._problem(parameters)
+        ws = self._workspace()
+        sbytes = self.lib.pb_gradient_scratch_bytes(self.N)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device="cuda")
+        g3 = (C.c_double * 3)()
+        self._factor_key = None
+        _lib.check(self.lib.pb_laplace_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w), _ptr(p),
+                                                _ptr(scratch), sbytes, g3))
+        del keep, scratch
+        d_scale, d_stretch, d_sigma = g3[0], g3[1], g3[2]
+        flat, rebuild = _flatten_scalars(prior_parameters)
+        base = self._spec(prior_parameters)
+        grads = []
+        for i, t in enumerate(flat):
+            h = 1e-6 * max(1.0, abs(t))
+            up, dn = list(flat), list(flat)
+            up[i], dn[i] = t + h, t - h
+            su, sd = self._spec(rebuild(up)), self._spec(rebuild(dn))
+            if (su.stretch_in != sd.stretch_in or su.period != sd.period or su.base != base.base
+                    or su.periodic != base.periodic):
+                raise NotImplementedError("gradients w.r.t. the period / inner stretch of a periodic kernel are not implemented")
+            grads.append(d_scale * (su.scale - sd.scale) / (2 * h) + d_stretch * (su.stretch_out - sd.stretch_out) / (2 * h))
+        g_prior = rebuild(grads)
+        if self._kind == _lib.PB_LIK_GAUSSIAN:
+            g_lik = (d_sigma,)
+        else:
+            g_lik = (None, None)
+        return value, (g_prior, g_lik)
+    return vg
+
+
+LaplaceGP.value_and_grad = _laplace_value_and_grad
 
 
 class VBGP(Approximator):

@@ -91,6 +91,8 @@ __device__ __forceinline__ double block_sum(double v) {
 // (M == N required).  Pointers 16-byte aligned, leading dimensions even.
 int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
             const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only);
+int gemm_nt_mode(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only);
 
 // potrf.cu
 int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
@@ -106,6 +108,13 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
              double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
 int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale);
+int gram_deriv_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+                      const double* K, int64_t ldk, const double* v, double* y);
+int64_t gram_deriv_partial_doubles(int64_t n);
+int gram_deriv_dots(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+                    const double* K, int64_t ldk, const double* Binv, int64_t ldb, const double* a, const double* s,
+                    double* partial, double* out);
+int set_identity(cudaStream_t stream, double* A, int64_t n, int64_t ld);
 int transform_block(cudaStream_t stream, const double* K, int64_t ldk, const double* s, double a, double jitter,
                     int64_t row0, int64_t col0, int64_t rows, int64_t cols, double* out, int64_t ldo);
 int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, const double* s, double a,

@@ -33,7 +33,7 @@ struct Layout {
 };
 
 enum VecSlot { V_W = 0, V_WN, V_F, V_S, V_B, V_T, V_C, V_X, V_G, V_SF, V_E, V_R, V_Z, V_P, V_Q, V_Y, V_U, V_COUNT };
-enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_PBP, S_RZ0, S_RZ1, S_RR, S_R0, S_COUNT = 16 };
+enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_PBP, S_RZ0, S_RZ1, S_RR, S_R0, S_G0, S_G1, S_G2, S_GD0, S_GD1, S_GSIG, S_COUNT = 16 };
 
 Layout make_layout(int64_t n, int D) {
     Layout L;
@@ -292,6 +292,45 @@ pcg_dir_kernel(const double* __restrict__ sc_new, const double* __restrict__ sc_
                int64_t n, double* __restrict__ p) {
     const double beta = *sc_new / *sc_old;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) p[i] = fma(beta, p[i], z[i]);
+}
+
+// ---- evidence-gradient helpers (oracle/gradients.py) ----
+// s2_i = 1/2 V_i d3_i with V_i = (1 - Binv_ii) / W_i = diag((K^-1 + W)^-1);
+// partials: [0] Gaussian d(-Psi)/dsigma terms  sum(-1/sigma + (y-f)^2/sigma^3 + V_i/sigma^3), [1] #(W_i <= 0)
+__global__ void __launch_bounds__(256)
+grad_s2_kernel(const double* __restrict__ Binv, int64_t ldb, const double* __restrict__ W, const double* __restrict__ d3,
+               const double* __restrict__ f, const void* __restrict__ y, int gaussian, double sigma, int64_t n,
+               double* __restrict__ s2, double* __restrict__ partial) {
+    double acc = 0, bad = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double w = W[i];
+        if (!(w > 0.0)) bad += 1.0;
+        const double V = (1.0 - Binv[i * ldb + i]) / w;
+        s2[i] = 0.5 * V * d3[i];
+        if (gaussian) {
+            const double r = reinterpret_cast<const double*>(y)[i] - f[i];
+            acc += -1.0 / sigma + (r * r + V) / (sigma * sigma * sigma);
+        }
+    }
+    write_partials(acc, bad, partial);
+}
+
+// out = a - b
+__global__ void __launch_bounds__(256)
+sub_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = a[i] - b[i];
+}
+
+// partials: a.b and c.d
+__global__ void __launch_bounds__(256)
+dot2_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+            const double* __restrict__ d, int64_t n, double* __restrict__ partial) {
+    double p = 0, q = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        p = fma(a[i], b[i], p);
+        q = fma(c[i], d[i], q);
+    }
+    write_partials(p, q, partial);
 }
 
 int check_problem(const pb_problem* prob) {
@@ -689,5 +728,85 @@ extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void
             PB_CUDA(cudaGetLastError());
         }
     }
+    return PB_OK;
+}
+
+// d objective / d (scale, stretch_out, sigma) at the converged weight: the closed form that replaces JAX's
+// reverse pass through fixed_point_layer (probit/implicit/solvers.py:28-64, approximators.py:132-134).
+// PRECONDITION: the workspace holds K(theta) and the Cholesky factor of B(w*) (pb_laplace_fit with
+// final_factor = 1 was the last call).  The factor is consumed (the buffer ends holding B^-1).
+// grad_host[0] = dPsi/dscale, [1] = dPsi/dstretch_out, [2] = dPsi/dsigma (NaN unless Gaussian).
+extern "C" int64_t pb_gradient_scratch_bytes(int64_t n) {
+    const int64_t ld = round_up(n > 0 ? n : 1, 16);
+    const int64_t part = gram_deriv_partial_doubles(n) * 8;
+    return n * ld * 8 > part ? n * ld * 8 : part;
+}
+
+extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
+                                   const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
+                                   double* grad_host) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    PB_CHECK(weight && precision && grad_host, PB_ERR_INVALID, "laplace_gradient: null argument");
+    PB_CHECK(scratch && scratch_bytes >= pb_gradient_scratch_bytes(prob->n), PB_ERR_INVALID, "laplace_gradient: scratch too small");
+    PB_CHECK((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, PB_ERR_INVALID, "laplace_gradient: scratch must be 256-byte aligned");
+    lik::Params lp;
+    PB_TRY(lik::make_params(prob->lik, lp));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const int Df = feature_dim(prob->kernel, prob->D);
+    const unsigned nb = vec_blocks(n);
+    const bool gaussian = prob->lik.kind == PB_LIK_GAUSSIAN;
+    double* U = reinterpret_cast<double*>(scratch);
+    double* sc = ws.scalars();
+    double *f = ws.vec(V_F), *g = ws.vec(V_G), *d3 = ws.vec(V_U), *sv = ws.vec(V_S);
+
+    PB_TRY(gemv(st, ws.K(), n, n, ld, weight, f));
+    PB_TRY(likelihood(st, prob->lik, f, prob->y, n, 1, nullptr, g, nullptr, d3));
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, sv, ws.partial()); pb::note_launch();
+    // b_c * c = K g ;  b_l * l = (K o rho) g
+    PB_TRY(gemv(st, ws.K(), n, n, ld, g, ws.vec(V_B)));
+    PB_TRY(gram_deriv_matvec(st, prob->kernel, ws.Z(), n, Df, Df, ws.K(), ld, g, ws.vec(V_T)));
+    // s3 = b - K (s o B^-1 (s o b)) for both (still with the Cholesky factor in place)
+    auto s3 = [&](double* b, double* out) -> int {
+        mul_kernel<<<nb, 256, 0, st>>>(sv, b, n, ws.vec(V_C)); pb::note_launch();
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
+        PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
+        mul_kernel<<<nb, 256, 0, st>>>(sv, ws.vec(V_C), n, ws.vec(V_X)); pb::note_launch();
+        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_X), ws.vec(V_Y)));
+        sub_kernel<<<nb, 256, 0, st>>>(b, ws.vec(V_Y), n, out); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        return PB_OK;
+    };
+    PB_TRY(s3(ws.vec(V_B), ws.vec(V_R)));       // s3_c * c
+    PB_TRY(s3(ws.vec(V_T), ws.vec(V_Z)));       // s3_l * l
+    // U = L^-T (upper) in scratch, then B^-1 = U U^T (lower) over the factor
+    PB_TRY(set_identity(st, U, n, ld));
+    PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), U, n, ld));
+    PB_TRY(gemm_nt_mode(st, n, n, n, 1.0, U, ld, U, ld, 0.0, ws.B(), ld, 2));
+    grad_s2_kernel<<<nb, 256, 0, st>>>(ws.B(), ld, precision, d3, f, prob->y, gaussian ? 1 : 0, prob->lik.sigma, n,
+                                       ws.vec(V_P), ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_GSIG, sc + S_BAD));
+    // lower-triangle sums (partials reuse the scratch: U is no longer needed)
+    PB_TRY(gram_deriv_dots(st, prob->kernel, ws.Z(), n, Df, Df, ws.K(), ld, ws.B(), ld, weight, sv, U, sc + S_G0));
+    dot2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_P), ws.vec(V_R), ws.vec(V_P), ws.vec(V_Z), n, ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_GD0, sc + S_GD1));
+    dot2_kernel<<<nb, 256, 0, st>>>(f, weight, f, weight, n, ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_FTW, nullptr));
+    double host[S_COUNT];
+    PB_TRY(read_scalars(st, ws, host, nullptr));
+    if (host[S_BAD] > 0) {
+        set_error("laplace_gradient: %d precisions are not positive (V = (1 - Binv_ii) / W undefined)", (int)host[S_BAD]);
+        return PB_ERR_NUMERIC;
+    }
+    const double c = prob->kernel.scale, l = prob->kernel.stretch_out;
+    const double dZ_c = (0.5 * host[S_FTW] - 0.5 * host[S_G2] + host[S_GD0]) / c;
+    const double dZ_l = (0.5 * host[S_G0] - 0.5 * host[S_G1] + host[S_GD1]) / l;
+    grad_host[0] = -dZ_c;
+    grad_host[1] = -dZ_l;
+    grad_host[2] = gaussian ? -host[S_GSIG] : NAN;
     return PB_OK;
 }

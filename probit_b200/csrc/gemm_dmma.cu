@@ -166,7 +166,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     const int m0 = tile_m * BM, n0 = tile_n * BN;
     if (m0 >= M || n0 >= N) return;               // whole CTA leaves together (2:1 lower rasterisation overshoot)
-    const int kblocks = (K + BK - 1) / BK;
+    // lower_only == 2: A and B are upper triangular (U U^T): every k < m0 contributes zero to this tile
+    const int k_begin = (lower_only == 2) ? (m0 / BK) * BK : 0;
+    const int kblocks = (K - k_begin + BK - 1) / BK;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -188,8 +190,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t full = bar_base + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t dstA = smem_base + s * STAGE_BYTES;
-        tma_load_2d(dstA, &mapA, kb * BK, m0, full);
-        tma_load_2d(dstA + A_STAGE_BYTES, &mapB, kb * BK, n0, full);
+        tma_load_2d(dstA, &mapA, k_begin + kb * BK, m0, full);
+        tma_load_2d(dstA + A_STAGE_BYTES, &mapB, k_begin + kb * BK, n0, full);
     };
     int next_kb = kblocks < STAGES ? kblocks : STAGES;             // first k-block not yet requested (thread 0)
     if (threadIdx.x == 0) {
@@ -346,7 +348,7 @@ int make_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, i
 
 template <class CF>
 int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
-           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
+           const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only) {
     static bool configured = false;
     if (!configured) {
         PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
@@ -380,7 +382,7 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
         PB_CUDA(cudaEventRecord(e0, stream));
     }
     gemm_nt_kernel<CF><<<(unsigned)blocks, CF::THREADS, CF::SMEM_BYTES, stream>>>(
-        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only ? 1 : 0, tn); pb::note_launch();
+        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only, tn); pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, stream));
         // algorithmic flops: 2MNK, or the lower triangle N(N+1)K for the SYRK form
@@ -394,6 +396,13 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
 
 int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
             const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {
+    return gemm_nt_mode(stream, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, lower_only ? 1 : 0);
+}
+
+// mode 0: full; 1: lower tiles only; 2: lower tiles only AND both operands upper triangular (C = U U^T:
+// k-blocks left of the tile's first row are skipped, N^3/3 instead of N^3 flops).
+int gemm_nt_mode(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                 const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only) {
     if (M <= 0 || N <= 0) return PB_OK;
     PB_CHECK(K > 0, PB_ERR_INVALID, "gemm_nt: K must be positive");
     PB_CHECK(alpha != 0.0, PB_ERR_INVALID, "gemm_nt: alpha must be non-zero");

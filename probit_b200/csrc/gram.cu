@@ -262,6 +262,125 @@ transform_block_kernel(const double* __restrict__ K, int64_t ldk, const double* 
     }
 }
 
+// ---- kernel-derivative reductions for the evidence gradient (probit/implicit/solvers.py:52-64 replaced by
+// the closed form of Rasmussen & Williams Alg. 5.1; oracle/gradients.py) ---------------------------------
+// For a stationary kernel K = c * base(rho), rho^2 = ||z_i - z_j||^2 with z = features / l:
+//   dK/dc = K / c,   dK/dl = K * rho^2 / l (EQ)  |  K * rho / l (Exp).
+// The kernels below stream K (and B^{-1}) once and regenerate rho from the staged features.
+__device__ __forceinline__ double rho_term(int base, double r2) { return base == PB_BASE_EQ ? r2 : sqrt(r2); }
+
+// y[i] = sum_j K_ij * rho_term_ij * v_j  (the l-derivative matvec, up to the 1/l factor); one 64-row tile per CTA
+__global__ void __launch_bounds__(256)
+gram_deriv_matvec_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, const double* __restrict__ K,
+                         int64_t ldk, int base, const double* __restrict__ v, double* __restrict__ y) {
+    extern __shared__ __align__(16) double sm[];
+    double* si = sm;
+    double* sj = sm + Df * TILE;
+    double* sv = sj + Df * TILE;           // v for the current column tile [64]
+    const int64_t i0 = (int64_t)blockIdx.x * TILE;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    stage_features(si, Z, ldz, i0, n, Df);
+    double rowacc[4] = {0, 0, 0, 0};
+    for (int64_t j0 = 0; j0 < n; j0 += TILE) {
+        __syncthreads();
+        stage_features(sj, Z, ldz, j0, n, Df);
+        if (threadIdx.x < TILE) sv[threadIdx.x] = (j0 + threadIdx.x < n) ? v[j0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        double acc[4][4];
+        tile_distances(si, sj, Df, ty, tx, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int64_t row = i0 + ty + 16 * r;
+            if (row >= n) continue;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int lc = 2 * tx + 32 * (c >> 1) + (c & 1);
+                if (j0 + lc < n) rowacc[r] = fma(K[row * ldk + j0 + lc] * rho_term(base, acc[r][c]), sv[lc], rowacc[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double a = rowacc[r];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        const int64_t row = i0 + ty + 16 * r;
+        if (tx == 0 && row < n) y[row] = a;
+    }
+}
+
+// Over lower tiles (each off-diagonal pair counted twice):
+//   partial[3b+0] = sum a_i a_j K_ij rho_ij           (-> w^T dK/dl w * l)
+//   partial[3b+1] = sum s_i s_j Binv_ij K_ij rho_ij   (-> tr(R dK/dl) * l)
+//   partial[3b+2] = sum s_i s_j Binv_ij K_ij          (-> tr(R dK/dc) * c)
+__global__ void __launch_bounds__(256)
+gram_deriv_dots_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, const double* __restrict__ K,
+                       int64_t ldk, const double* __restrict__ Binv, int64_t ldb, int base,
+                       const double* __restrict__ a, const double* __restrict__ s, double* __restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double* si = sm;
+    double* sj = sm + Df * TILE;
+    int ti, tj;
+    tri_tile(blockIdx.x, ti, tj);
+    const int64_t i0 = (int64_t)ti * TILE, j0 = (int64_t)tj * TILE;
+    stage_features(si, Z, ldz, i0, n, Df);
+    stage_features(sj, Z, ldz, j0, n, Df);
+    __syncthreads();
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    double acc[4][4];
+    tile_distances(si, sj, Df, ty, tx, acc);
+    double p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t row = i0 + ty + 16 * r;
+        if (row >= n) continue;
+        const double ai = a[row], sr = s[row];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int64_t col = j0 + 2 * tx + 32 * (c >> 1) + (c & 1);
+            if (col > row || col >= n) continue;
+            const double wgt = (col == row) ? 1.0 : 2.0;
+            const double k = K[row * ldk + col];
+            const double kr = k * rho_term(base, acc[r][c]);
+            const double sb = wgt * sr * s[col] * Binv[row * ldb + col];
+            p0 = fma(wgt * ai * a[col], kr, p0);
+            p1 = fma(sb, kr, p1);
+            p2 = fma(sb, k, p2);
+        }
+    }
+    p0 = block_sum<256>(p0);
+    p1 = block_sum<256>(p1);
+    p2 = block_sum<256>(p2);
+    if (threadIdx.x == 0) {
+        partial[3 * (int64_t)blockIdx.x] = p0;
+        partial[3 * (int64_t)blockIdx.x + 1] = p1;
+        partial[3 * (int64_t)blockIdx.x + 2] = p2;
+    }
+}
+
+__global__ void __launch_bounds__(1024)
+sum3_kernel(const double* __restrict__ partial, int64_t nblk, double* __restrict__ out) {
+    double a = 0, b = 0, c = 0;
+    for (int64_t i = threadIdx.x; i < nblk; i += 1024) {
+        a += partial[3 * i];
+        b += partial[3 * i + 1];
+        c += partial[3 * i + 2];
+    }
+    a = block_sum<1024>(a);
+    b = block_sum<1024>(b);
+    c = block_sum<1024>(c);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = c; }
+}
+
+__global__ void __launch_bounds__(256)
+identity_kernel(double* __restrict__ A, int64_t n, int64_t ld) {
+    for (int64_t row = blockIdx.y; row < n; row += gridDim.y)
+        for (int64_t c = blockIdx.x * 256ll + threadIdx.x; c < n; c += (int64_t)gridDim.x * 256)
+            A[row * ld + c] = (c == row) ? 1.0 : 0.0;
+}
+
 inline int64_t tri_tiles(int64_t n) {
     const int64_t T = ceil_div<int64_t>(n, TILE);
     return T * (T + 1) / 2;
@@ -337,6 +456,51 @@ int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, 
                   double jitter, double* B, int64_t ldb) {
     if (n == 0) return PB_OK;
     sym_transform_kernel<<<(unsigned)tri_tiles(n), 256, 0, stream>>>(K, n, ldk, s, a, jitter, B, ldb); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int gram_deriv_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+                      const double* K, int64_t ldk, const double* v, double* y) {
+    if (n == 0) return PB_OK;
+    const int smem = (2 * Df * TILE + TILE) * 8;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(gram_deriv_matvec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * MAX_DF * TILE + TILE) * 8));
+        PB_CUDA(cudaFuncSetAttribute(gram_deriv_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GRAM_SMEM_CROSS_MAX));
+        configured = true;
+    }
+    gram_deriv_matvec_kernel<<<(unsigned)ceil_div<int64_t>(n, TILE), 256, smem, stream>>>(Z, n, Df, ldz, K, ldk, spec.base, v, y); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// out[0..2] (device) = the three lower-triangle sums of gram_deriv_dots_kernel; `partial` needs 3*tri_tiles(n) doubles
+int64_t gram_deriv_partial_doubles(int64_t n) { return 3 * tri_tiles(n); }
+
+int gram_deriv_dots(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
+                    const double* K, int64_t ldk, const double* Binv, int64_t ldb, const double* a, const double* s,
+                    double* partial, double* out) {
+    if (n == 0) return PB_OK;
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(gram_deriv_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     GRAM_SMEM_CROSS_MAX));
+        configured = true;
+    }
+    const int64_t tiles = tri_tiles(n);
+    gram_deriv_dots_kernel<<<(unsigned)tiles, 256, gram_smem_cross(Df), stream>>>(Z, n, Df, ldz, K, ldk, Binv, ldb, spec.base, a, s, partial); pb::note_launch();
+    sum3_kernel<<<1, 1024, 0, stream>>>(partial, tiles, out); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int set_identity(cudaStream_t stream, double* A, int64_t n, int64_t ld) {
+    if (n == 0) return PB_OK;
+    dim3 grid((unsigned)(ceil_div<int64_t>(n, 256) < 64 ? ceil_div<int64_t>(n, 256) : 64), (unsigned)(n < 32768 ? n : 32768));
+    identity_kernel<<<grid, 256, 0, stream>>>(A, n, ld); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -182,3 +182,43 @@ def test_block_cyclic_factorization_hook_single_gpu():
     # and the hook is gone afterwards
     w2, _ = p.approximate_posterior(params)
     assert relerr(w2.cpu().numpy(), w_ref) < TOL
+
+
+def test_value_and_grad_matches_oracle_gradient():
+    """value_and_grad (closed-form evidence gradient on the GPU) against oracle/gradients.py, which is itself
+    pinned to finite differences of the oracle objective (tests/test_oracle_gradient.py)."""
+    from oracle import gradients as OG
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    # ordinal, Matern12 with (lengthscale, scale) prior parameters
+    X, y, params, _ = ordinal_problem(5, 400, 3, 5, "matern12")
+    lik = params[1]
+    th = (0.8, 1.4)
+    prior_o = lambda t: t[1] * OK.Matern12().stretch(t[0])
+    prior_p = lambda t: t[1] * PK.Matern12().stretch(t[0])
+    o = OA.LaplaceGP((X, y), prior_o, OU.log_probit_likelihood, tolerance=1e-9)
+    p = PA.LaplaceGP((X, y), prior_p, PU.log_probit_likelihood, tolerance=1e-9)
+    w_ref = o.weight((th, lik))
+    G = OG.laplace_gradient(prior_o(th)(X), X, y, w_ref, lik,
+                            dict(base="exp", periodic=0, scale=th[1], stretch_in=1.0, period=1.0, stretch_out=th[0]), False)
+    value, (g_prior, g_lik) = p.value_and_grad()((th, lik))
+    assert abs(value - o.objective()((th, lik))) < TOL * abs(value)
+    assert abs(g_prior[0] - G["stretch_out"]) < 1e-7 * max(1.0, abs(G["stretch_out"]))
+    assert abs(g_prior[1] - G["scale"]) < 1e-7 * max(1.0, abs(G["scale"]))
+    assert g_lik == (None, None)
+    # a bare-scalar prior parameter (examples/classification.py:414-417): d/dl only
+    p2 = PA.LaplaceGP((X, y), lambda l: 1.4 * PK.Matern12().stretch(l), PU.log_probit_likelihood, tolerance=1e-9)
+    v2, (g2, _) = p2.value_and_grad()((0.8, lik))
+    assert abs(g2 - G["stretch_out"]) < 1e-7 * max(1.0, abs(G["stretch_out"]))
+    # regression: periodic EQ, Gaussian likelihood, all three hyper-parameters (examples/regression.py:139-143)
+    Xr, yr, _, fam = regression_problem(0, 20)
+    pr_o, pr_p = make_prior(OK, fam), make_prior(PK, fam)
+    par = ((0.3, 0.8), (0.25,))
+    orf = OA.LaplaceGP((Xr, yr), pr_o, OU.log_gaussian_likelihood, tolerance=1e-10)
+    wr = orf.weight(par)
+    Gr = OG.laplace_gradient(pr_o(par[0])(Xr), Xr, yr, wr, par[1],
+                             dict(base="eq", periodic=1, scale=0.8, stretch_in=1.0, period=0.5, stretch_out=0.3), True)
+    pg = PA.LaplaceGP((Xr, yr), pr_p, PU.log_gaussian_likelihood, tolerance=1e-10)
+    val, (gp_, gl_) = pg.value_and_grad()(par)
+    assert abs(gp_[0] - Gr["stretch_out"]) < 1e-7 * abs(Gr["stretch_out"])
+    assert abs(gp_[1] - Gr["scale"]) < 1e-7 * abs(Gr["scale"])
+    assert abs(gl_[0] - Gr["sigma"]) < 1e-7 * abs(Gr["sigma"])

@@ -1,0 +1,48 @@
+"""Pins the oracle's closed-form evidence gradient (oracle/gradients.py) against central finite differences of
+the oracle objective — the same numerical check the reference plots (examples/classification.py:104-111). CPU only."""
+import numpy as np
+import pytest
+
+from helpers import make_prior, ordinal_problem, regression_problem
+from oracle import approximators as OA, gradients as OG, kernels as OK, utilities as OU
+
+
+def _fd(fun, x, h=1e-5):
+    return (fun(x + h) - fun(x - h)) / (2 * h)
+
+
+@pytest.mark.parametrize("family,base", [("eq_scaled", "eq"), ("matern_scaled", "exp")])
+def test_ordinal_gradient_matches_finite_differences(family, base):
+    X, y, params, _ = ordinal_problem(3, 150, 2, 3, "eq")
+    lik = params[1]
+    prior = make_prior(OK, "eq_scaled") if base == "eq" else (lambda th: th[1] * OK.Matern12().stretch(th[0]))
+
+    def obj(l, c):
+        gp = OA.LaplaceGP((X, y), prior, OU.log_probit_likelihood, tolerance=1e-10)
+        return gp.objective(jitter=0.0)(((l, c), lik))
+
+    l, c = 0.9, 1.3
+    gp = OA.LaplaceGP((X, y), prior, OU.log_probit_likelihood, tolerance=1e-10)
+    w = gp.weight(((l, c), lik))
+    G = OG.laplace_gradient(prior((l, c))(X), X, y, w, lik,
+                            dict(base=base, periodic=0, scale=c, stretch_in=1.0, period=1.0, stretch_out=l), False)
+    assert abs(G["stretch_out"] - _fd(lambda t: obj(t, c), l)) < 1e-6 * max(1, abs(G["stretch_out"]))
+    assert abs(G["scale"] - _fd(lambda t: obj(l, t), c)) < 1e-6 * max(1, abs(G["scale"]))
+
+
+def test_gaussian_periodic_gradient_matches_finite_differences():
+    X, y, _, family = regression_problem(0, 20)
+    prior = make_prior(OK, family)
+
+    def obj(l, c, s):
+        gp = OA.LaplaceGP((X, y), prior, OU.log_gaussian_likelihood, tolerance=1e-10)
+        return gp.objective(jitter=0.0)(((l, c), (s,)))
+
+    l, c, s = 0.3, 0.8, 0.25
+    gp = OA.LaplaceGP((X, y), prior, OU.log_gaussian_likelihood, tolerance=1e-10)
+    w = gp.weight(((l, c), (s,)))
+    G = OG.laplace_gradient(prior((l, c))(X), X, y, w, (s,),
+                            dict(base="eq", periodic=1, scale=c, stretch_in=1.0, period=0.5, stretch_out=l), True)
+    assert abs(G["stretch_out"] - _fd(lambda t: obj(t, c, s), l)) < 1e-6 * abs(G["stretch_out"])
+    assert abs(G["scale"] - _fd(lambda t: obj(l, t, s), c)) < 1e-6 * abs(G["scale"])
+    assert abs(G["sigma"] - _fd(lambda t: obj(l, c, t), s)) < 1e-6 * abs(G["sigma"])

@@ -95,7 +95,8 @@ int pb_likelihood(pb_stream_t stream, const pb_likelihood_spec* lik, const doubl
                   int64_t n, int64_t batch, double* ll, double* g, double* h, double* d3);
 
 /* ---- K1/K2: Gram assembly ---------------------------------------------------------------------
- * pb_features: Z[n x Df] = phi(X[n x D]); Df = pb_feature_dim(spec, D).
+ * pb_features: Z[Df x n] = phi(X[n x D]) stored FEATURE-MAJOR (Z[d * ldz + i], ldz >= n);
+ *              Df = pb_feature_dim(spec, D).
  * pb_gram_sym: K = k(X,X) (+ diag_scalar I) (+ diag(diag_vec)); both triangles written (mirror
  *              store); replaces `prior(theta)(X)` at Laplace.py:7,21,24, VB.py:7,22.
  * pb_gram_cross: K[n1 x n2] = k(X1, X2); replaces `kernel(X_train, X_test)` approximators.py:173.

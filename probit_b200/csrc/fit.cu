@@ -352,8 +352,8 @@ int bind(const pb_problem* prob, void* workspace, int64_t workspace_bytes, Ws& w
 
 int build_gram(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
     const int Df = feature_dim(prob->kernel, prob->D);
-    PB_TRY(features(st, prob->kernel, prob->X, prob->n, prob->D, prob->D, ws.Z(), Df));
-    return gram_sym(st, prob->kernel, ws.Z(), prob->n, Df, Df, ws.K(), ws.L.ld, nullptr, 0.0);
+    PB_TRY(features(st, prob->kernel, prob->X, prob->n, prob->D, prob->D, ws.Z(), prob->n));
+    return gram_sym(st, prob->kernel, ws.Z(), prob->n, Df, prob->n, ws.K(), ws.L.ld, nullptr, 0.0);
 }
 
 int finalize(cudaStream_t st, const Ws& ws, unsigned nblk, double* out0, double* out1) {
@@ -716,13 +716,13 @@ extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void
     const double kss = prob->kernel.scale;    // kernel.elwise(x*, x*) of a stationary kernel (approximators.py:172)
     for (int64_t r0 = 0; r0 < n_test; r0 += chunk) {
         const int64_t m = n_test - r0 < chunk ? n_test - r0 : chunk;
-        PB_TRY(features(st, prob->kernel, X_test + r0 * D, m, D, D, Zs, Df));
+        PB_TRY(features(st, prob->kernel, X_test + r0 * D, m, D, D, Zs, chunk));
         // K_*f tile (approximators.py:173, transposed: test points are rows)
-        PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, Df, Df, V, ld, nullptr));
+        PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, chunk, n, V, ld, nullptr));
         PB_TRY(gemv(st, V, m, n, ld, weight, mean + r0));                                   // approximators.py:179
         if (variance) {
             // var = k** - || L_B^{-1} (s o k_*) ||^2  ==  Kss - einsum(Kfs, solve(K + P^-1, Kfs)) (approximators.py:175-178)
-            PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, Df, Df, V, ld, ws.vec(V_S)));
+            PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, chunk, n, V, ld, ws.vec(V_S)));
             PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), V, m, ld));
             row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(m, 8), 256, 0, st>>>(V, m, n, ld, kss, variance + r0); pb::note_launch();
             PB_CUDA(cudaGetLastError());
@@ -766,7 +766,7 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, sv, ws.partial()); pb::note_launch();
     // b_c * c = K g ;  b_l * l = (K o rho) g
     PB_TRY(gemv(st, ws.K(), n, n, ld, g, ws.vec(V_B)));
-    PB_TRY(gram_deriv_matvec(st, prob->kernel, ws.Z(), n, Df, Df, ws.K(), ld, g, ws.vec(V_T)));
+    PB_TRY(gram_deriv_matvec(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, g, ws.vec(V_T)));
     // s3 = b - K (s o B^-1 (s o b)) for both (still with the Cholesky factor in place)
     auto s3 = [&](double* b, double* out) -> int {
         mul_kernel<<<nb, 256, 0, st>>>(sv, b, n, ws.vec(V_C)); pb::note_launch();
@@ -789,7 +789,7 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, sc + S_GSIG, sc + S_BAD));
     // lower-triangle sums (partials reuse the scratch: U is no longer needed)
-    PB_TRY(gram_deriv_dots(st, prob->kernel, ws.Z(), n, Df, Df, ws.K(), ld, ws.B(), ld, weight, sv, U, sc + S_G0));
+    PB_TRY(gram_deriv_dots(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, ws.B(), ld, weight, sv, U, sc + S_G0));
     dot2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_P), ws.vec(V_R), ws.vec(V_P), ws.vec(V_Z), n, ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, sc + S_GD0, sc + S_GD1));

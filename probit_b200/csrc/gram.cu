@@ -5,7 +5,7 @@
 // probit/approximators.py:174,272,337 and `kernel(X_train, X_test)` at approximators.py:173.
 //
 //  1. pb_features maps inputs once: Z = T(X / stretch_in) / stretch_out (T = periodic sin/cos
-//     feature map or identity), so the N^2 loop contains no trigonometry.
+//     feature map or identity), stored feature-major (Df x n), so the N^2 loop contains no trigonometry.
 //  2. gram kernels evaluate r^2 = sum_d (z_id - z_jd)^2 with exact differences (no GEMM expansion:
 //     SURVEY.md §7.2(b) — the expansion form puts O(1e-8) noise on diag(K) for Matern12) in 64x64
 //     tiles, 4x4 outputs per thread, features staged in shared memory, 256-byte coalesced row
@@ -34,25 +34,64 @@ features_kernel(const double* __restrict__ X, int64_t n, int D, int64_t ldx, dou
             const double a = TWO_PI * u / period;
             double s, c;
             sincos(a, &s, &c);
-            Z[i * ldz + d] = s / stretch_out;
-            Z[i * ldz + D + d] = c / stretch_out;
+            Z[(int64_t)d * ldz + i] = s / stretch_out;
+            Z[(int64_t)(D + d) * ldz + i] = c / stretch_out;
         } else {
-            Z[i * ldz + d] = u / stretch_out;
+            Z[(int64_t)d * ldz + i] = u / stretch_out;
         }
     }
 }
 
-__device__ __forceinline__ double base_eval(int base, double scale, double r2) {
-    return base == PB_BASE_EQ ? scale * exp(-0.5 * r2) : scale * exp(-sqrt(r2));
+// exp(-x) for x >= 0 without the special-case handling of the library exp (the Gram kernels are issue
+// bound on FP64 transcendentals, ncu: sm__throughput 74 %, 110 instructions per element with libm exp+sqrt).
+// Cody-Waite reduction with fdlibm's ln2 split, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
+// 4e-18), exponent added directly to the high word; underflows to 0 beyond 2^-1020.  <= 2 ulp.
+__device__ __forceinline__ double exp_neg(double x) {
+    const double MAGIC = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
+    const double t = fma(-x, 1.4426950408889634, MAGIC);
+    const int n = __double2loint(t);                          // n = round(-x log2 e) <= 0
+    const double nf = t - MAGIC;
+    double r = fma(nf, -6.93147180369123816490e-01, -x);      // -x - n ln2_hi (exact product)
+    r = fma(nf, -1.90821492927058770002e-10, r);              //      - n ln2_lo
+    double p = 1.6059043836821613e-10;                        // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                      // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                     // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                     // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                    // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                      // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                     // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                     // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                     // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                    // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                    // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+    return n < -1020 ? 0.0 : res;
 }
 
-// Loads the features of 64 rows starting at row0 into s[d*64 + r] (zero beyond n).
+template <int BASE>
+__device__ __forceinline__ double base_eval_t(double scale, double r2) {
+    if (BASE == PB_BASE_EQ) return scale * exp_neg(0.5 * r2);
+    const double rho = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;
+    return scale * exp_neg(rho);
+}
+
+__device__ __forceinline__ double base_eval(int base, double scale, double r2) {
+    if (base == PB_BASE_EQ) return scale * exp_neg(0.5 * r2);
+    const double rho = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;       // sqrt(r2), ~1.5 ulp, no denormal/NaN fix-up code
+    return scale * exp_neg(rho);
+}
+
+// Loads the features of 64 points starting at row0 into s[d*64 + r] (zero beyond n).  Features are stored
+// feature-major, Z[d * ldz + i], so this is a straight coalesced copy with shift/mask index math only.
 __device__ __forceinline__ void stage_features(double* s, const double* __restrict__ Z, int64_t ldz, int64_t row0,
                                                int64_t n, int Df) {
     for (int e = threadIdx.x; e < TILE * Df; e += 256) {
-        const int r = e / Df, d = e % Df;
+        const int d = e >> 6, r = e & (TILE - 1);
         const int64_t i = row0 + r;
-        s[d * TILE + r] = i < n ? Z[i * ldz + d] : 0.0;
+        s[e] = i < n ? Z[(int64_t)d * ldz + i] : 0.0;
     }
 }
 
@@ -92,9 +131,14 @@ __device__ __forceinline__ void tri_tile(int64_t b, int& ti, int& tj) {
     tj = (int)(b - r * (r + 1) / 2);
 }
 
+// BASE: kernel family at compile time (no per-element branch); FULL: n is a multiple of 64 and ldk is even,
+// so every tile is interior and no bounds check is compiled in.  One tile per CTA: a persistent variant with
+// register-prefetched features was measured 15-20 % SLOWER (two barriers per tile serialise the three
+// resident CTAs; the hardware overlaps independent one-tile CTAs better).
+template <int BASE, bool FULL>
 __global__ void __launch_bounds__(256)
 gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, double* __restrict__ K, int64_t ldk,
-                int base, double scale, const double* __restrict__ diag_vec, double diag_scalar) {
+                double scale, const double* __restrict__ diag_vec, double diag_scalar) {
     extern __shared__ __align__(16) double sm[];
     double* si = sm;                   // [Df][64]
     double* sj = sm + Df * TILE;       // [Df][64]
@@ -111,7 +155,7 @@ gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, do
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = base_eval(base, scale, acc[r][c]);
+        for (int c = 0; c < 4; ++c) acc[r][c] = base_eval_t<BASE>(scale, acc[r][c]);
 
     const bool diag_tile = ti == tj;
     if (diag_tile) {
@@ -120,22 +164,22 @@ gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, do
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const int row = ty + 16 * r, col = 2 * tx + 32 * (c >> 1) + (c & 1);
-                if (row == col && i0 + row < n)
+                if (row == col && (FULL || i0 + row < n))
                     acc[r][c] += diag_scalar + (diag_vec ? diag_vec[i0 + row] : 0.0);
             }
     }
-    const bool full_cols = (j0 + TILE <= n) && ((ldk & 1) == 0);
+    const bool full_cols = FULL || ((j0 + TILE <= n) && ((ldk & 1) == 0));
+    double* kbase = K + (i0 + ty) * ldk + j0 + 2 * tx;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int64_t row = i0 + ty + 16 * r;
-        if (row >= n) continue;
+        if (!FULL && i0 + ty + 16 * r >= n) continue;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            const int64_t col = j0 + 2 * tx + 32 * c;
-            double* p = K + row * ldk + col;
+            double* p = kbase + (int64_t)(16 * r) * ldk + 32 * c;
             if (full_cols) {
                 *reinterpret_cast<double2*>(p) = make_double2(acc[r][2 * c], acc[r][2 * c + 1]);
             } else {
+                const int64_t col = j0 + 2 * tx + 32 * c;
                 if (col < n) p[0] = acc[r][2 * c];
                 if (col + 1 < n) p[1] = acc[r][2 * c + 1];
             }
@@ -148,19 +192,19 @@ gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, do
 #pragma unroll
         for (int c = 0; c < 4; ++c) T[(2 * tx + 32 * (c >> 1) + (c & 1)) * (TILE + 1) + ty + 16 * r] = acc[r][c];
     __syncthreads();
-    const bool full_rows = (i0 + TILE <= n) && ((ldk & 1) == 0);
+    const bool full_rows = FULL || ((i0 + TILE <= n) && ((ldk & 1) == 0));
+    double* mbase = K + (j0 + ty) * ldk + i0 + 2 * tx;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int64_t row = j0 + ty + 16 * r;      // always < n because tj < ti
+    for (int r = 0; r < 4; ++r) {            // rows j0 + ty + 16 r are always < n because tj < ti
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int lc = 2 * tx + 32 * c;
-            const int64_t col = i0 + lc;
             const double v0 = T[(ty + 16 * r) * (TILE + 1) + lc], v1 = T[(ty + 16 * r) * (TILE + 1) + lc + 1];
-            double* p = K + row * ldk + col;
+            double* p = mbase + (int64_t)(16 * r) * ldk + 32 * c;
             if (full_rows) {
                 *reinterpret_cast<double2*>(p) = make_double2(v0, v1);
             } else {
+                const int64_t col = i0 + lc;
                 if (col < n) p[0] = v0;
                 if (col + 1 < n) p[1] = v1;
             }
@@ -423,13 +467,27 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
     PB_TRY(check_spec(spec));
     PB_CHECK(Df >= 1 && Df <= MAX_DF, PB_ERR_UNSUPPORTED, "feature dimension %d exceeds %d", Df, MAX_DF);
     if (n == 0) return PB_OK;
-    static bool configured = false;
-    if (!configured) {
-        PB_CUDA(cudaFuncSetAttribute(gram_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM_SYM_MAX));
-        configured = true;
+    const bool full = (n % TILE == 0) && ((ldk & 1) == 0) && ((reinterpret_cast<uintptr_t>(K) & 15) == 0);
+    const unsigned grid = (unsigned)tri_tiles(n);
+    const int smem = gram_smem_sym(Df);
+#define PB_LAUNCH_GRAM_SYM(BASE, FULL)                                                                              \
+    do {                                                                                                           \
+        static bool configured = false;                                                                            \
+        if (!configured) {                                                                                         \
+            PB_CUDA(cudaFuncSetAttribute(gram_sym_kernel<BASE, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                         GRAM_SMEM_SYM_MAX));                                                      \
+            configured = true;                                                                                     \
+        }                                                                                                          \
+        gram_sym_kernel<BASE, FULL><<<grid, 256, smem, stream>>>(Z, n, Df, ldz, K, ldk, spec.scale, diag_vec,       \
+                                                                 diag_scalar);                                     \
+    } while (0)
+    if (spec.base == PB_BASE_EQ) {
+        if (full) PB_LAUNCH_GRAM_SYM(PB_BASE_EQ, true); else PB_LAUNCH_GRAM_SYM(PB_BASE_EQ, false);
+    } else {
+        if (full) PB_LAUNCH_GRAM_SYM(PB_BASE_EXP, true); else PB_LAUNCH_GRAM_SYM(PB_BASE_EXP, false);
     }
-    gram_sym_kernel<<<(unsigned)tri_tiles(n), 256, gram_smem_sym(Df), stream>>>(Z, n, Df, ldz, K, ldk, spec.base,
-                                                                           spec.scale, diag_vec, diag_scalar); pb::note_launch();
+#undef PB_LAUNCH_GRAM_SYM
+    pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -59,8 +59,8 @@ def features(spec, X):
     X = _mat2(X)
     n, D = X.shape
     Df = lib.pb_feature_dim(C.byref(spec), D)
-    Z = torch.empty((n, Df), dtype=torch.float64, device="cuda")
-    _lib.check(lib.pb_features(_stream(), C.byref(spec), _ptr(X), n, D, D, _ptr(Z), Df))
+    Z = torch.empty((Df, n), dtype=torch.float64, device="cuda")      # feature-major: Z[d, i]
+    _lib.check(lib.pb_features(_stream(), C.byref(spec), _ptr(X), n, D, D, _ptr(Z), n))
     return Z
 
 
@@ -68,17 +68,17 @@ def gram(spec, X, Y=None, diag_add=0.0, diag_vec=None):
     """K(X, X) (+ diag_add I + diag(diag_vec)) or K(X, Y); returns an (n, m) view with padded ld."""
     lib = _lib.load()
     Zx = features(spec, X)
-    n, Df = Zx.shape
+    Df, n = Zx.shape
     if Y is None:
         K = empty_matrix(n, n)
         dv = _dev(diag_vec) if diag_vec is not None else None
-        _lib.check(lib.pb_gram_sym(_stream(), C.byref(spec), _ptr(Zx), n, Df, Df, _ptr(K), _ld(K), _ptr(dv),
+        _lib.check(lib.pb_gram_sym(_stream(), C.byref(spec), _ptr(Zx), n, Df, n, _ptr(K), _ld(K), _ptr(dv),
                                    float(diag_add)))
         return K
     Zy = features(spec, Y)
-    m = Zy.shape[0]
+    m = Zy.shape[1]
     K = empty_matrix(n, m)
-    _lib.check(lib.pb_gram_cross(_stream(), C.byref(spec), _ptr(Zx), n, _ptr(Zy), m, Df, Df, Df, _ptr(K), _ld(K)))
+    _lib.check(lib.pb_gram_cross(_stream(), C.byref(spec), _ptr(Zx), n, _ptr(Zy), m, Df, n, m, _ptr(K), _ld(K)))
     return K
 
 

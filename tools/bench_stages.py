@@ -27,6 +27,12 @@ out = {"peaks": {"hbm_gbs": HBM, "fp64_dmma_tflops": DMMA}}
 which = sys.argv[1:] or ["gram", "likelihood", "predictive", "predict", "c3"]
 
 if "gram" in which:
+    # write-only reference: torch fill_ over the same 32 GiB (what an ideal Gram kernel is bounded by)
+    buf = torch.empty(65536 * 65536, dtype=torch.float64, device="cuda")
+    ms = best_ms(lambda: buf.fill_(1.0))
+    out["write_only_fill_32GiB"] = {"ms": ms, "GBs": buf.numel() * 8 / ms * 1e-6, "frac_hbm": buf.numel() * 8 / ms * 1e-6 / HBM}
+    del buf
+    torch.cuda.empty_cache()
     for n, D, fam in [(16384, 8, "eq"), (65536, 4, "matern12")]:
         X = torch.rand(n, D, dtype=torch.float64, device="cuda")
         spec = (1.0 * (PK.EQ() if fam == "eq" else PK.Matern12()).stretch(1.0)).lower()
@@ -34,7 +40,7 @@ if "gram" in which:
         K = linalg.empty_matrix(n, n)
         lib = _lib.load()
         import ctypes as C
-        f = lambda: lib.pb_gram_sym(linalg._stream(), C.byref(spec), linalg._ptr(Z), n, Z.shape[1], Z.shape[1], linalg._ptr(K), K.stride(0), None, 0.0)
+        f = lambda: lib.pb_gram_sym(linalg._stream(), C.byref(spec), linalg._ptr(Z), n, Z.shape[0], n, linalg._ptr(K), K.stride(0), None, 0.0)
         ms = best_ms(f)
         gbs = 8.0 * n * n / ms * 1e-6
         out[f"gram_{fam}_N{n}_D{D}"] = {"ms": ms, "GBs": gbs, "frac_hbm": gbs / HBM, "algorithmic_bytes": 8.0 * n * n}

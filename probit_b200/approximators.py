@@ -135,8 +135,13 @@ class Approximator(ABC):
         from . import linalg
         return linalg.symv(self._K_view(), _dev(weight))
 
-    def predict(self, X_test, parameters, weight, precision):
-        """approximators.py:154-180: (mean, variance) of the latent GP at X_test, both (N_test,)."""
+    def predict(self, X_test, parameters, weight, precision, variance=True):
+        """approximators.py:154-180: (mean, variance) of the latent GP at X_test, both (N_test,).
+
+        `variance=False` (extension) skips the factorisation and the N^2 * N_test variance solve and returns
+        (mean, None): the mean-only sweep over very large test sets (BASELINE configs[4])."""
+        if not variance:
+            return self._predict_mean(X_test, parameters, weight), None
         prob, keep = self._problem(parameters)
         ws = self._workspace()
         weight = _dev(weight).reshape(-1)
@@ -164,6 +169,23 @@ class Approximator(ABC):
                                        _ptr(scratch), scratch_bytes, _ptr(mean), _ptr(var)))
         del keep
         return mean, var
+
+    def _predict_mean(self, X_test, parameters, weight):
+        prob, keep = self._problem(parameters)
+        ws = self._ensure_gram(prob)                  # features of the training inputs (and K) in the workspace
+        weight = _dev(weight).reshape(-1)
+        X_test = _mat2(X_test)
+        if X_test.shape[1] != self.D:
+            raise ValueError("X_test has the wrong input dimension")
+        n_test = X_test.shape[0]
+        chunk = self.predict_chunk or max(1, min(n_test, max(256, (1 << 31) // (8 * max(self.N, 1)))))
+        scratch_bytes = self.lib.pb_predict_scratch_bytes(self.N, self.D, chunk)
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device="cuda")
+        mean = torch.empty(n_test, dtype=torch.float64, device="cuda")
+        _lib.check(self.lib.pb_predict(_stream(), C.byref(prob), _ptr(ws), _ptr(weight), _ptr(X_test), n_test, chunk,
+                                       _ptr(scratch), scratch_bytes, _ptr(mean), None))
+        del keep
+        return mean
 
     def approximate_posterior(self, parameters):
         """approximators.py:204-210."""

@@ -89,7 +89,7 @@ __device__ __forceinline__ void mm64_acc(const double* A, const double* B, int t
 
 __global__ void __launch_bounds__(256)
 tb_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const double* __restrict__ dinv,
-                  double* __restrict__ tinv) {
+                  double* __restrict__ tinv, double* __restrict__ tinv_t) {
     extern __shared__ double tsm[];
     double* Xc = tsm;                          // X_rp for r = p, p+1, p+2   [3][64][65]
     double* A = tsm + 3 * LEAF * TLD;          // staged L_qr / Dinv_q        [64][65]
@@ -98,8 +98,9 @@ tb_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const do
     const int nv = (int)(n - j0 < TB ? n - j0 : TB);
     const int nq = (nv + LEAF - 1) / LEAF;
     double* out = tinv + (int64_t)blockIdx.x * TB * TB;
+    double* out_t = tinv_t + (int64_t)blockIdx.x * TB * TB;      // X^T (upper), so the backward solve reads rows too
     const int tid = threadIdx.x, ti = tid >> 4, tk = tid & 15;
-    for (int e = tid; e < TB * TB; e += 256) out[e] = 0.0;
+    for (int e = tid; e < TB * TB; e += 256) { out[e] = 0.0; out_t[e] = 0.0; }
     __syncthreads();
     for (int p = 0; p < nq; ++p) {
         const double* dp = dinv + (j0 / LEAF + p) * LEAF * LEAF;
@@ -108,6 +109,7 @@ tb_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const do
             const double v = dp[e];
             Xc[i * TLD + k] = v;
             out[(p * LEAF + i) * TB + p * LEAF + k] = v;
+            out_t[(p * LEAF + k) * TB + p * LEAF + i] = v;
         }
         __syncthreads();
         for (int q = p + 1; q < nq; ++q) {
@@ -138,6 +140,7 @@ tb_inverse_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const do
                 for (int v = 0; v < 4; ++v) {
                     const int i = ti + 16 * u, k = tk + 16 * v;
                     out[(q * LEAF + i) * TB + p * LEAF + k] = -x[u][v];
+                    out_t[(p * LEAF + k) * TB + q * LEAF + i] = -x[u][v];
                     if (q - p <= 2) Xc[(q - p) * LEAF * TLD + i * TLD + k] = -x[u][v];
                 }
             __syncthreads();
@@ -167,15 +170,22 @@ __device__ __forceinline__ void tinv_matvec_fwd(const double* __restrict__ X, co
     __syncthreads();
 }
 
-// x = X^T v (backward): thread (col = t % 256, group = t / 256) sums rows r = col + group, step 4
-// (coalesced across the 256 columns for every r); the four partials meet in shared memory.
-__device__ __forceinline__ void tinv_matvec_bwd(const double* __restrict__ X, const double* sv, double* sx, double* red) {
-    const int col = threadIdx.x & (TB - 1), grp = threadIdx.x >> 8;
-    double acc = 0.0;
-    for (int r = col + grp; r < TB; r += 4) acc = fma(X[(int64_t)r * TB + col], sv[r], acc);
-    red[grp * TB + col] = acc;
-    __syncthreads();
-    if (grp == 0) sx[col] = (red[col] + red[TB + col]) + (red[2 * TB + col] + red[3 * TB + col]);
+// x = X^T v (backward) using the transposed inverse XT (upper, row-major): the same warp-per-row dot product.
+__device__ __forceinline__ void tinv_matvec_bwd(const double* __restrict__ XT, const double* sv, double* sx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int u = 0; u < TB / 32; ++u) {
+        const int r = warp + 32 * u;
+        const double* row = XT + (int64_t)r * TB;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < TB / 32; ++k) {
+            const int c = lane + 32 * k;
+            if (c >= r) acc = fma(row[c], sv[c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) sx[r] = acc;
+    }
     __syncthreads();
 }
 
@@ -253,7 +263,7 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const doub
     if (bootstrap) {                                // x_last = L_last^{-T} y_last
         if (threadIdx.x < TB) sv[threadIdx.x] = threadIdx.x < nvj ? y[j0 + threadIdx.x] : 0.0;
         __syncthreads();
-        tinv_matvec_bwd(tinv + (j0 / TB) * TB * TB, sv, sx, red);
+        tinv_matvec_bwd(tinv + (j0 / TB) * TB * TB, sv, sx);
         if (threadIdx.x < nvj) x[j0 + threadIdx.x] = sx[threadIdx.x];
         return;
     }
@@ -265,7 +275,7 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const doub
     {
         const int r_lo = grp * 32, r_hi = min(nvj, r_lo + 32);
         const double* lp = L + (j0 + r_lo) * ldl + c;
-#pragma unroll 8
+#pragma unroll 16
         for (int r = r_lo; r < r_hi; ++r) {
             const double2 v = __ldcs(reinterpret_cast<const double2*>(lp));
             acc.x = fma(v.x, sx[r], acc.x);
@@ -287,7 +297,7 @@ trsv_bwd_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, const doub
     const int64_t p0 = j0 - TB;                      // previous (upper) block, always full width
     if (threadIdx.x < TB) sv[threadIdx.x] = y[p0 + threadIdx.x];
     __syncthreads();
-    tinv_matvec_bwd(tinv + (p0 / TB) * TB * TB, sv, sx, red);
+    tinv_matvec_bwd(tinv + (p0 / TB) * TB * TB, sv, sx);
     if (threadIdx.x < TB) x[p0 + threadIdx.x] = sx[threadIdx.x];
 }
 
@@ -317,6 +327,7 @@ int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const dou
              "trsv: factor must be 16-byte aligned with an even leading dimension");
     const int64_t nblk = ceil_div<int64_t>(n, TB);
     const double* tinv = dinv + ceil_div<int64_t>(n, LEAF) * LEAF * LEAF;     // TB-block inverses follow the leaf inverses
+    if (trans) tinv += nblk * TB * TB;                                        // ... and their transposes follow those
     if (!trans) {
         trsv_fwd_kernel<<<1, TSV_THREADS, 0, stream>>>(L, n, ldl, tinv, -1, rhs, x); pb::note_launch();
         for (int64_t jb = 0; jb + 1 < nblk; ++jb) {
@@ -345,7 +356,8 @@ int build_block_inverses(cudaStream_t stream, const double* L, int64_t n, int64_
         configured = true;
     }
     double* tinv = dinv + ceil_div<int64_t>(n, LEAF) * LEAF * LEAF;
-    tb_inverse_kernel<<<(unsigned)ceil_div<int64_t>(n, TB), 256, TBINV_SMEM, stream>>>(L, n, ldl, dinv, tinv); pb::note_launch();
+    const int64_t nblk = ceil_div<int64_t>(n, TB);
+    tb_inverse_kernel<<<(unsigned)nblk, 256, TBINV_SMEM, stream>>>(L, n, ldl, dinv, tinv, tinv + nblk * TB * TB); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -352,10 +352,11 @@ int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, 
 }  // namespace pb
 
 extern "C" int64_t pb_potrf_workspace_bytes(int64_t n) {
-    // [ceil(n/64) leaf inverses, 64x64] followed by [ceil(n/256) diagonal-block inverses, 256x256] (blas2.cu)
+    // [ceil(n/64) leaf inverses, 64x64] followed by [ceil(n/256) diagonal-block inverses, 256x256] and their
+    // transposes (blas2.cu)
     const int64_t leaves = (n + pb::LEAF - 1) / pb::LEAF;
     const int64_t blocks = (n + 255) / 256;
-    return ((leaves > 0 ? leaves : 1) * pb::LEAF * pb::LEAF + (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
+    return ((leaves > 0 ? leaves : 1) * pb::LEAF * pb::LEAF + 2 * (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
 }
 
 extern "C" int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,

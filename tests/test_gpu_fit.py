@@ -222,3 +222,14 @@ def test_value_and_grad_matches_oracle_gradient():
     assert abs(gp_[0] - Gr["stretch_out"]) < 1e-7 * abs(Gr["stretch_out"])
     assert abs(gp_[1] - Gr["scale"]) < 1e-7 * abs(Gr["scale"])
     assert abs(gl_[0] - Gr["sigma"]) < 1e-7 * abs(Gr["sigma"])
+
+
+def test_predict_mean_only_matches_full_predict():
+    X, y, params, family = ordinal_problem(9, 300, 2, 3, "eq")
+    o, p = _pair(X, y, family)
+    w, prec = p.approximate_posterior(params)
+    Xs = np.random.default_rng(4).uniform(-0.5, 1.5, size=(1000, 2))
+    m_full, _ = p.predict(Xs, params, w, prec)
+    p2 = _pair(X, y, family)[1]                      # fresh object: no Gram / factor cached
+    m_only, v_none = p2.predict(Xs, params, w, prec, variance=False)
+    assert v_none is None and relerr(m_only.cpu().numpy(), m_full.cpu().numpy()) < 1e-13

@@ -60,8 +60,8 @@ if "gram" in which:
         ms = timeit(lambda: linalg.gram(k, X))
         out[f"gram_{fam}_{n}_D{D}_ms"] = ms
         out[f"gram_{fam}_{n}_D{D}_GBs"] = 8.0 * n * n / ms * 1e-6
-if "blas2" in which:
-    n = 32768
+if "blas2" in which or "blas2_64k" in which:
+    n = 65536 if "blas2_64k" in which else 32768
     A = linalg.empty_matrix(n, n); A.normal_()
     x = torch.randn(n, dtype=torch.float64, device="cuda")
     ms = timeit(lambda: linalg.symv(A, x))

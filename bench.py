@@ -305,7 +305,10 @@ def run_ours(args):
         "roofline": {
             "bound": "tensor", "kernel": "gemm_nt_kernel<128x64, 8 warps, 2 CTA/SM> (Cholesky trailing update / TRSM / predict solve)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": None, "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
+            "traffic": 3.03e9, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch of this kernel "
+                                                "(SYRK 16384 x 512, algorithmic 2.21e9 B; profiles/r01_gemm_main_ncu.md); the kernel is "
+                                                "tensor-bound, launches in the timed region vary in shape"),
+            "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
             "algorithmic_flops_per_step": g_fl.value / args.steps,
         },
         "cholesky": {"n": n, "per_step": n_potrf, "flops_each": n ** 3 / 3.0,

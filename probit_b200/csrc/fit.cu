@@ -527,7 +527,12 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         // preconditioner (rescaled by s_fac/s) and refactor only if PCG stalls.
         const double* xsol = ws.vec(V_C);
         bool solved = false;
-        if (have_factor && it >= 1 && pcg_enabled(n)) {
+        if (have_factor && prob->lik.kind == PB_LIK_GAUSSIAN) {
+            // W = 1/sigma^2 does not depend on f: B is the matrix already factored, reuse it as is
+            PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
+            PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
+            solved = true;
+        } else if (have_factor && it >= 1 && pcg_enabled(n)) {
             int used = -1;
             PB_TRY(pcg_solve(st, ws, n, ws.vec(V_S), ws.vec(V_C), 48, 1e-13, &used));
             if (used >= 0) {

@@ -21,6 +21,11 @@ from . import _lib, kernels as _kernels, utilities as _util
 from .linalg import _dev, _mat2, _ptr, _stream
 
 
+def _is_float32(x):
+    dt = getattr(x, "dtype", None)
+    return dt is not None and str(dt).endswith("float32")
+
+
 def _likelihood_kind(log_likelihood, grad_log_likelihood, hessian_log_likelihood):
     if log_likelihood is _util.log_gaussian_likelihood:
         if grad_log_likelihood is not None or hessian_log_likelihood is not None:
@@ -58,6 +63,9 @@ class Approximator(ABC):
         self._kind = _likelihood_kind(log_likelihood, grad_log_likelihood, hessian_log_likelihood)
         self.lib = _lib.load()
         X_train, y_train = data
+        # float32 inputs (the reference without jax_enable_x64, BASELINE configs[0]) are promoted to float64 on the
+        # device — the FP64 path is the product — and results are handed back in the input precision.
+        self.out_dtype = torch.float32 if _is_float32(X_train) else torch.float64
         self.X = _mat2(X_train)
         (self.N, self.D) = self.X.shape                 # approximators.py:108
         self.y = _util._labels(self._kind, y_train)
@@ -168,7 +176,7 @@ class Approximator(ABC):
         _lib.check(self.lib.pb_predict(_stream(), C.byref(prob), _ptr(ws), _ptr(weight), _ptr(X_test), n_test, chunk,
                                        _ptr(scratch), scratch_bytes, _ptr(mean), _ptr(var)))
         del keep
-        return mean, var
+        return mean.to(self.out_dtype), var.to(self.out_dtype)
 
     def _predict_mean(self, X_test, parameters, weight):
         prob, keep = self._problem(parameters)
@@ -185,12 +193,12 @@ class Approximator(ABC):
         _lib.check(self.lib.pb_predict(_stream(), C.byref(prob), _ptr(ws), _ptr(weight), _ptr(X_test), n_test, chunk,
                                        _ptr(scratch), scratch_bytes, _ptr(mean), None))
         del keep
-        return mean
+        return mean.to(self.out_dtype)
 
     def approximate_posterior(self, parameters):
         """approximators.py:204-210."""
         w, p, _ = self._fit(parameters, final_factor=False)
-        return w, p
+        return w.to(self.out_dtype), p.to(self.out_dtype)
 
     def value_and_grad(self):
         """approximators.py:132-134: callable(parameters) -> (objective, gradient with the structure of `parameters`)."""

@@ -108,6 +108,9 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
              double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
 int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale);
+int gram_matvec_splits(int64_t n1);
+int gram_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
+                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, const double* v, double* partial, double* y);
 int gram_deriv_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t n, int Df, int64_t ldz,
                       const double* K, int64_t ldk, const double* v, double* y);
 int64_t gram_deriv_partial_doubles(int64_t n);

@@ -698,7 +698,7 @@ extern "C" int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, co
 
 extern "C" int64_t pb_predict_scratch_bytes(int64_t n, int D, int64_t chunk) {
     const int64_t ld = round_up(n > 0 ? n : 1, 16);
-    return round_up(chunk * ld * 8, 256) + round_up(chunk * 2 * (int64_t)D * 8, 256) + 256;
+    return round_up(chunk * ld * 8, 256) + round_up(chunk * 2 * (int64_t)D * 8, 256) + round_up(64 * chunk * 8, 256) + 256;
 }
 
 extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace, const double* weight,
@@ -718,13 +718,13 @@ extern "C" int pb_predict(pb_stream_t stream, const pb_problem* prob, const void
     const int D = prob->D, Df = feature_dim(prob->kernel, D);
     double* V = reinterpret_cast<double*>(scratch);
     double* Zs = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + round_up(chunk * ld * 8, 256));
+    double* mean_partial = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(Zs) + round_up(chunk * 2 * (int64_t)D * 8, 256));
     const double kss = prob->kernel.scale;    // kernel.elwise(x*, x*) of a stationary kernel (approximators.py:172)
     for (int64_t r0 = 0; r0 < n_test; r0 += chunk) {
         const int64_t m = n_test - r0 < chunk ? n_test - r0 : chunk;
         PB_TRY(features(st, prob->kernel, X_test + r0 * D, m, D, D, Zs, chunk));
-        // K_*f tile (approximators.py:173, transposed: test points are rows)
-        PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, chunk, n, V, ld, nullptr));
-        PB_TRY(gemv(st, V, m, n, ld, weight, mean + r0));                                   // approximators.py:179
+        // mean = K_*f w (approximators.py:173,179): cross-covariance tiles generated in registers, never stored
+        PB_TRY(gram_matvec(st, prob->kernel, Zs, m, ws.Z(), n, Df, chunk, n, weight, mean_partial, mean + r0));
         if (variance) {
             // var = k** - || L_B^{-1} (s o k_*) ||^2  ==  Kss - einsum(Kfs, solve(K + P^-1, Kfs)) (approximators.py:175-178)
             PB_TRY(gram_cross(st, prob->kernel, Zs, m, ws.Z(), n, Df, chunk, n, V, ld, ws.vec(V_S)));

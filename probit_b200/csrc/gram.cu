@@ -306,6 +306,61 @@ transform_block_kernel(const double* __restrict__ K, int64_t ldk, const double* 
     }
 }
 
+// Fused predictive mean (probit/approximators.py:173,179: Kfs.T @ weight): partial[split][i] =
+// sum_{j in split} k(z1_i, z2_j) v_j with the cross-covariance tile generated in registers and never
+// written anywhere.  grid = (row tiles of 64 test points, column splits); a second tiny kernel adds the
+// splits in a fixed order (deterministic).
+template <int BASE>
+__global__ void __launch_bounds__(256)
+gram_matvec_kernel(const double* __restrict__ Z1, int64_t n1, const double* __restrict__ Z2, int64_t n2, int Df,
+                   int64_t ldz1, int64_t ldz2, double scale, const double* __restrict__ v, int64_t cols_per_split,
+                   double* __restrict__ partial) {
+    extern __shared__ __align__(16) double sm[];
+    double* si = sm;
+    double* sj = sm + Df * TILE;
+    double* sv = sj + Df * TILE;
+    const int64_t i0 = (int64_t)blockIdx.x * TILE;
+    const int64_t jbeg = (int64_t)blockIdx.y * cols_per_split;
+    const int64_t jend = jbeg + cols_per_split < n2 ? jbeg + cols_per_split : n2;
+    const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+    stage_features(si, Z1, ldz1, i0, n1, Df);
+    double rowacc[4] = {0, 0, 0, 0};
+    for (int64_t j0 = jbeg; j0 < jend; j0 += TILE) {
+        __syncthreads();
+        stage_features(sj, Z2, ldz2, j0, jend, Df);
+        if (threadIdx.x < TILE) sv[threadIdx.x] = (j0 + threadIdx.x < jend) ? v[j0 + threadIdx.x] : 0.0;
+        __syncthreads();
+        double acc[4][4];
+        tile_distances(si, sj, Df, ty, tx, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int lc = 2 * tx + 32 * (c >> 1) + (c & 1);
+                rowacc[r] = fma(base_eval_t<BASE>(scale, acc[r][c]), sv[lc], rowacc[r]);   // sv = 0 beyond the split
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        double a = rowacc[r];
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a += __shfl_xor_sync(0xffffffffu, a, 4);
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        const int64_t row = i0 + ty + 16 * r;
+        if (tx == 0 && row < n1) partial[(int64_t)blockIdx.y * n1 + row] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sum_splits_kernel(const double* __restrict__ partial, int splits, int64_t n, double* __restrict__ y) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        double a = 0.0;
+        for (int s = 0; s < splits; ++s) a += partial[(int64_t)s * n + i];
+        y[i] = a;
+    }
+}
+
 // ---- kernel-derivative reductions for the evidence gradient (probit/implicit/solvers.py:52-64 replaced by
 // the closed form of Rasmussen & Williams Alg. 5.1; oracle/gradients.py) ---------------------------------
 // For a stationary kernel K = c * base(rho), rho^2 = ||z_i - z_j||^2 with z = features / l:
@@ -514,6 +569,40 @@ int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, 
                   double jitter, double* B, int64_t ldb) {
     if (n == 0) return PB_OK;
     sym_transform_kernel<<<(unsigned)tri_tiles(n), 256, 0, stream>>>(K, n, ldk, s, a, jitter, B, ldb); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// y[i] = sum_j k(z1_i, z2_j) v_j without materialising the cross Gram; `partial` needs splits * n1 doubles
+int gram_matvec_splits(int64_t n1) {
+    const int64_t row_tiles = ceil_div<int64_t>(n1 > 0 ? n1 : 1, TILE);
+    int64_t s = ceil_div<int64_t>(4 * (int64_t)num_sms(), row_tiles);
+    return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
+}
+
+int gram_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
+                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, const double* v, double* partial, double* y) {
+    PB_TRY(check_spec(spec));
+    if (n1 == 0) return PB_OK;
+    const int splits = gram_matvec_splits(n1);
+    const int64_t cols = ceil_div<int64_t>(ceil_div<int64_t>(n2, splits), TILE) * TILE;
+    const int smem = (2 * Df * TILE + TILE) * 8;
+    dim3 grid((unsigned)ceil_div<int64_t>(n1, TILE), (unsigned)splits);
+    static bool configured = false;
+    if (!configured) {
+        PB_CUDA(cudaFuncSetAttribute(gram_matvec_kernel<PB_BASE_EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * MAX_DF * TILE + TILE) * 8));
+        PB_CUDA(cudaFuncSetAttribute(gram_matvec_kernel<PB_BASE_EXP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (2 * MAX_DF * TILE + TILE) * 8));
+        configured = true;
+    }
+    if (spec.base == PB_BASE_EQ)
+        gram_matvec_kernel<PB_BASE_EQ><<<grid, 256, smem, stream>>>(Z1, n1, Z2, n2, Df, ldz1, ldz2, spec.scale, v, cols, partial);
+    else
+        gram_matvec_kernel<PB_BASE_EXP><<<grid, 256, smem, stream>>>(Z1, n1, Z2, n2, Df, ldz1, ldz2, spec.scale, v, cols, partial);
+    pb::note_launch();
+    const int64_t want = ceil_div<int64_t>(n1, 256);
+    sum_splits_kernel<<<(unsigned)(want < 1024 ? want : 1024), 256, 0, stream>>>(partial, splits, n1, y); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -233,3 +233,19 @@ def test_predict_mean_only_matches_full_predict():
     p2 = _pair(X, y, family)[1]                      # fresh object: no Gram / factor cached
     m_only, v_none = p2.predict(Xs, params, w, prec, variance=False)
     assert v_none is None and relerr(m_only.cpu().numpy(), m_full.cpu().numpy()) < 1e-13
+
+
+def test_float32_inputs_are_promoted_and_returned_as_float32():
+    """BASELINE configs[0] runs the reference in float32; north_star tolerance 1e-4 there."""
+    import torch
+    X, y, params, family = regression_problem(0, 20)
+    o, _ = _pair(X, y, family, gaussian=True)
+    w_ref, p_ref = o.approximate_posterior(params)
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    p = PA.LaplaceGP((X.astype(np.float32), y.astype(np.float32)), make_prior(PK, family), PU.log_gaussian_likelihood)
+    w, prec = p.approximate_posterior(params)
+    assert w.dtype == torch.float32 and prec.dtype == torch.float32
+    assert relerr(w.cpu().numpy(), w_ref) < 1e-4
+    m, v = p.predict(np.linspace(-0.5, 1.5, 50, dtype=np.float32)[:, None], params, w, prec)
+    m_ref, v_ref = o.predict(np.linspace(-0.5, 1.5, 50)[:, None], params, w_ref, p_ref)
+    assert m.dtype == torch.float32 and relerr(m.cpu().numpy(), m_ref) < 1e-4 and np.abs(v.cpu().numpy() - v_ref).max() < 1e-4

@@ -204,6 +204,8 @@ typedef int (*pb_factor_fn)(void* user, pb_stream_t stream, const double* K, int
 int pb_set_factor_callback(pb_factor_fn fn, void* user);
 /* Build features + K(theta) into the workspace (what every fit does first); and locate K inside it. */
 int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
+/* Features of the training inputs only (all that a mean-only pb_predict with variance == NULL needs). */
+int pb_build_features(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
 int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk);
 int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
                    double jitter, int32_t final_factor, void* workspace, int64_t workspace_bytes,
@@ -239,6 +241,13 @@ int64_t pb_predict_scratch_bytes(int64_t n, int D, int64_t chunk);
 int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace, const double* weight,
                const double* X_test, int64_t n_test, int64_t chunk, void* scratch, int64_t scratch_bytes,
                double* mean, double* variance);
+
+/* Approximator.predict_covariance (approximators.py:182-197): full n_test x n_test posterior covariance
+ * K_** - V V^T, V = (s o K_*f) L_B^-T; same preconditions as pb_predict; scratch sized by
+ * pb_predict_scratch_bytes(n, D, n_test). */
+int pb_predict_covariance(pb_stream_t stream, const pb_problem* prob, const void* workspace,
+                          const double* X_test, int64_t n_test, void* scratch, int64_t scratch_bytes,
+                          double* cov, int64_t ldc);
 
 /* ---- K15: ordinal predictive distributions (probit/utilities.py:232-249) ----------------------
  * out[n_test x J] = Phi((b[j+1]-m)/s) - Phi((b[j]-m)/s), s = sqrt(var + sigma^2).                */

@@ -157,16 +157,7 @@ class Approximator(ABC):
         X_test = _mat2(X_test)
         if X_test.shape[1] != self.D:
             raise ValueError("X_test has the wrong input dimension")
-        key = self._spec_key(prob.kernel)
-        reuse_factor = (self._factor_key is not None and self._factor_key[0] == key
-                        and torch.equal(self._factor_key[1], precision))
-        if not reuse_factor:
-            info = C.c_int32(0)
-            reuse_gram = int(self._gram_key == key)
-            self._gram_key, self._factor_key = None, None
-            _lib.check(self.lib.pb_predict_prepare(_stream(), C.byref(prob), _ptr(precision), reuse_gram, _ptr(ws),
-                                                   self._ws_bytes, C.byref(info)))
-            self._gram_key, self._factor_key = key, (key, precision.clone())
+        ws = self._prepare_factor(prob, precision)
         n_test = X_test.shape[0]
         chunk = self.predict_chunk or max(1, min(n_test, max(256, (1 << 31) // (8 * max(self.N, 1)))))
         scratch_bytes = self.lib.pb_predict_scratch_bytes(self.N, self.D, chunk)
@@ -178,9 +169,43 @@ class Approximator(ABC):
         del keep
         return mean.to(self.out_dtype), var.to(self.out_dtype)
 
+    def _prepare_factor(self, prob, precision):
+        """Factor of B = I + P^1/2 K P^1/2 for (theta, precision) in the workspace (cached across calls)."""
+        ws = self._workspace()
+        key = self._spec_key(prob.kernel)
+        reuse_factor = (self._factor_key is not None and self._factor_key[0] == key
+                        and torch.equal(self._factor_key[1], precision))
+        if not reuse_factor:
+            info = C.c_int32(0)
+            reuse_gram = int(self._gram_key == key)
+            self._gram_key, self._factor_key = None, None
+            _lib.check(self.lib.pb_predict_prepare(_stream(), C.byref(prob), _ptr(precision), reuse_gram, _ptr(ws),
+                                                   self._ws_bytes, C.byref(info)))
+            self._gram_key, self._factor_key = key, (key, precision.clone())
+        return ws
+
+    def predict_covariance(self, X_test, parameters, weight, precision):
+        """approximators.py:182-197: full (N_test, N_test) posterior predictive covariance."""
+        from . import linalg
+        prob, keep = self._problem(parameters)
+        precision = _dev(precision).reshape(-1)
+        X_test = _mat2(X_test)
+        ws = self._prepare_factor(prob, precision)
+        n_test = X_test.shape[0]
+        sbytes = self.lib.pb_predict_scratch_bytes(self.N, self.D, n_test)
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device="cuda")
+        cov = linalg.empty_matrix(n_test, n_test)
+        _lib.check(self.lib.pb_predict_covariance(_stream(), C.byref(prob), _ptr(ws), _ptr(X_test), n_test, _ptr(scratch),
+                                                  sbytes, _ptr(cov), cov.stride(0)))
+        del keep
+        return cov.to(self.out_dtype)
+
     def _predict_mean(self, X_test, parameters, weight):
         prob, keep = self._problem(parameters)
-        ws = self._ensure_gram(prob)                  # features of the training inputs (and K) in the workspace
+        ws = self._workspace()
+        if self._gram_key != self._spec_key(prob.kernel):    # only the training features are needed, not K
+            self._gram_key, self._factor_key = None, None
+            _lib.check(self.lib.pb_build_features(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes))
         weight = _dev(weight).reshape(-1)
         X_test = _mat2(X_test)
         if X_test.shape[1] != self.D:

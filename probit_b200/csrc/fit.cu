@@ -481,6 +481,13 @@ extern "C" int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* w
     return build_gram(reinterpret_cast<cudaStream_t>(stream), prob, ws);
 }
 
+extern "C" int pb_build_features(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes) {
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    return features(reinterpret_cast<cudaStream_t>(stream), prob->kernel, prob->X, prob->n, prob->D, prob->D, ws.Z(),
+                    prob->n);
+}
+
 extern "C" int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk) {
     PB_CHECK(workspace && K && ldk, PB_ERR_INVALID, "workspace_gram: null argument");
     const Layout L = make_layout(n, D);
@@ -814,4 +821,29 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     grad_host[1] = -dZ_l;
     grad_host[2] = gaussian ? -host[S_GSIG] : NAN;
     return PB_OK;
+}
+
+// predict_covariance (probit/approximators.py:182-197): C = K_** - K_*f (K + P^-1)^-1 K_f* for n_test points
+// = K_** - V V^T with V = (s o K_*f) L_B^-T.  Needs the factor from pb_predict_prepare.  `scratch` holds V
+// (pb_predict_scratch_bytes(n, D, n_test)); `cov` is n_test x ldc, full (both triangles) on return.
+extern "C" int pb_predict_covariance(pb_stream_t stream, const pb_problem* prob, const void* workspace,
+                                     const double* X_test, int64_t n_test, void* scratch, int64_t scratch_bytes,
+                                     double* cov, int64_t ldc) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    PB_TRY(check_problem(prob));
+    PB_CHECK(workspace && X_test && cov && n_test >= 1, PB_ERR_INVALID, "predict_covariance: bad argument");
+    PB_CHECK(scratch && scratch_bytes >= pb_predict_scratch_bytes(prob->n, prob->D, n_test), PB_ERR_INVALID,
+             "predict_covariance: scratch too small");
+    Ws ws;
+    ws.L = make_layout(prob->n, prob->D);
+    ws.base = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(workspace));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const int D = prob->D, Df = feature_dim(prob->kernel, D);
+    double* V = reinterpret_cast<double*>(scratch);
+    double* Zs = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + round_up(n_test * ld * 8, 256));
+    PB_TRY(features(st, prob->kernel, X_test, n_test, D, D, Zs, n_test));
+    PB_TRY(gram_sym(st, prob->kernel, Zs, n_test, Df, n_test, cov, ldc, nullptr, 0.0));                  // K_**
+    PB_TRY(gram_cross(st, prob->kernel, Zs, n_test, ws.Z(), n, Df, n_test, n, V, ld, ws.vec(V_S)));       // s o K_*f
+    PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), V, n_test, ld));
+    return gemm_nt(st, n_test, n_test, n, -1.0, V, ld, V, ld, 1.0, cov, ldc, false);
 }

@@ -249,3 +249,16 @@ def test_float32_inputs_are_promoted_and_returned_as_float32():
     m, v = p.predict(np.linspace(-0.5, 1.5, 50, dtype=np.float32)[:, None], params, w, prec)
     m_ref, v_ref = o.predict(np.linspace(-0.5, 1.5, 50)[:, None], params, w_ref, p_ref)
     assert m.dtype == torch.float32 and relerr(m.cpu().numpy(), m_ref) < 1e-4 and np.abs(v.cpu().numpy() - v_ref).max() < 1e-4
+
+
+def test_predict_covariance_matches_oracle():
+    X, y, params, family = ordinal_problem(13, 260, 2, 3, "eq")
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)
+    Xs = np.random.default_rng(6).uniform(-0.5, 1.5, size=(70, 2))
+    C_ref = o.predict_covariance(Xs, params, w_ref, p_ref)
+    w, prec = p.approximate_posterior(params)
+    Cg = p.predict_covariance(Xs, params, w, prec).cpu().numpy()
+    assert np.abs(Cg - C_ref).max() < 1e-9 * max(1.0, np.abs(C_ref).max())
+    m, v = p.predict(Xs, params, w, prec)
+    assert np.abs(np.diag(Cg) - v.cpu().numpy()).max() < 1e-10

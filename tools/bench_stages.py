@@ -97,6 +97,23 @@ if "predict" in which:
     del gp
     torch.cuda.empty_cache()
 
+if "predict_mean" in which:
+    # BASELINE configs[4] (mean part): 10^7 test points against N=65536 training points, cross-covariance generated on
+    # the fly inside the fused matvec kernel (6.6e11 kernel evaluations; nothing but X*, w and the mean touches HBM)
+    n, nt, D = 65536, 10_000_000, 4
+    rng = np.random.default_rng(0)
+    X = rng.uniform(size=(n, D)); y = rng.integers(0, 5, size=n)
+    cut = np.array([-np.inf, -0.9, -0.2, 0.3, 1.0, np.inf])
+    gp = PA.LaplaceGP((X, y), lambda l: 1.0 * PK.Matern12().stretch(l), PU.log_probit_likelihood, predict_chunk=65536)
+    params = (1.0, (0.63, cut))
+    w = torch.randn(n, dtype=torch.float64, device="cuda") * 0.01
+    Xs = torch.rand(nt, D, dtype=torch.float64, device="cuda") * 2 - 0.5
+    ms = best_ms(lambda: gp.predict(Xs, params, w, None, variance=False), reps=2)
+    out["predict_mean_N65536_Ntest1e7"] = {"ms": ms, "kernel_evals_per_s": float(n) * nt / ms * 1e3,
+                                           "test_points_per_s": nt / ms * 1e3}
+    del gp, Xs
+    torch.cuda.empty_cache()
+
 if "c3" in which:
     # BASELINE configs[2]: GP regression N=16384, D=8, EQ, FP64: Gram + Cholesky + evidence (LaplaceGP, Gaussian likelihood)
     n, D = 16384, 8

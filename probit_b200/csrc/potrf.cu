@@ -214,8 +214,12 @@ int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
 int potrf_block_size(int64_t n) {
     const int forced = opt_potrf_nb();
     if (forced > 0) return forced / 64 * 64 > 0 ? forced / 64 * 64 : 64;
+    // measured on B200 (tools/potrf_sweep.py): N=65536: 512 -> 34.2, 768 -> 34.7, 1024 -> 34.9 TFLOP/s;
+    // deeper panels raise the SYRK's K (fewer C round trips) and the look-ahead hides the longer panel chain
     if (n <= 2048) return 256;
-    return 512;
+    if (n < 24576) return 512;
+    if (n < 49152) return 768;
+    return 1024;
 }
 
 namespace {

@@ -262,3 +262,46 @@ def test_predict_covariance_matches_oracle():
     assert np.abs(Cg - C_ref).max() < 1e-9 * max(1.0, np.abs(C_ref).max())
     m, v = p.predict(Xs, params, w, prec)
     assert np.abs(np.diag(Cg) - v.cpu().numpy()).max() < 1e-10
+
+
+@pytest.mark.parametrize("N,D,J,family", [(6, 1, 2, "eq"), (64, 3, 4, "matern12"), (65, 2, 3, "eq"), (257, 8, 5, "matern12")])
+def test_small_and_boundary_sizes(N, D, J, family):
+    X, y, params, _ = ordinal_problem(N + 100, N, D, J, family)
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)
+    w, prec = p.approximate_posterior(params)
+    assert p.last_result.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+    Xs = np.random.default_rng(N).uniform(-0.5, 1.5, size=(3, D))
+    m_ref, v_ref = o.predict(Xs, params, w_ref, p_ref)
+    m, v = p.predict(Xs, params, w, prec)
+    assert relerr(m.cpu().numpy(), m_ref) < TOL and np.abs(v.cpu().numpy() - v_ref).max() < 1e-9
+    ov, pv = _pair(X, y, family, cls="VBGP")
+    wv_ref, _ = ov.approximate_posterior(params)
+    wv, _ = pv.approximate_posterior(params)
+    assert pv.last_result.iterations == len(ov.trace) and relerr(wv.cpu().numpy(), wv_ref) < TOL
+
+
+def test_nan_inputs_raise_numeric_error_not_garbage():
+    from probit_b200 import _lib
+    X, y, params, family = ordinal_problem(2, 90, 2, 3, "eq")
+    X = X.copy()
+    X[7, 1] = np.nan
+    _, p = _pair(X, y, family)
+    with pytest.raises(_lib.NumericError):
+        p.approximate_posterior(params)
+
+
+def test_periodic_high_dimensional_features():
+    """D=8 periodic -> 16 features: Gaussian likelihood, closed-form check."""
+    rng = np.random.default_rng(3)
+    X = rng.uniform(size=(120, 8))
+    yv = np.sin(X.sum(1)) + 0.1 * rng.standard_normal(120)
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    prior_o = lambda th: th[1] * OK.EQ().stretch(th[0]).periodic(0.7)
+    prior_p = lambda th: th[1] * PK.EQ().stretch(th[0]).periodic(0.7)
+    par = ((1.5, 0.9), (0.2,))
+    p = PA.LaplaceGP((X, yv), prior_p, PU.log_gaussian_likelihood)
+    w, prec = p.approximate_posterior(par)
+    K = prior_o(par[0])(X)
+    assert relerr(w.cpu().numpy(), np.linalg.solve(K + 0.04 * np.eye(120), yv)) < 1e-9

@@ -134,29 +134,29 @@ int main(int argc, char** argv) {
         cudaFree(A); cudaFree(B); cudaFree(C);
     }
 
-    // cuSOLVER potrf comparator on a diagonally dominant SPD matrix
+    // cuSOLVER potrf comparator on a diagonally dominant SPD matrix (64-bit API: N=65536 overflows the int one)
     cusolverDnHandle_t sh; cusolverDnCreate(&sh);
-    for (int n = 8192; n <= potrf_max; n *= 2) {
+    cusolverDnParams_t params; cusolverDnCreateParams(&params);
+    for (int64_t n = 8192; n <= potrf_max; n *= 2) {
         double* A; CK(cudaMalloc(&A, sizeof(double) * (size_t)n * n));
         std::vector<double> diag(n, (double)n);
-        int lwork = 0; cusolverDnDpotrf_bufferSize(sh, CUBLAS_FILL_MODE_LOWER, n, A, n, &lwork);
-        double* work; CK(cudaMalloc(&work, sizeof(double) * lwork));
+        size_t wdev = 0, whost = 0;
+        cusolverDnXpotrf_bufferSize(sh, params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A, n, CUDA_R_64F, &wdev, &whost);
+        void* work; CK(cudaMalloc(&work, wdev ? wdev : 8));
+        std::vector<char> hwork(whost ? whost : 8);
         int* info; CK(cudaMalloc(&info, sizeof(int)));
-        auto reset = [&] {
-            CK(cudaMemset(A, 0, sizeof(double) * (size_t)n * n));
-            CK(cudaMemcpy2D(A, sizeof(double) * (n + 1), diag.data(), sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice));
-        };
         float best = 1e30f;
         for (int r = 0; r < 2; ++r) {
-            reset();
+            CK(cudaMemset(A, 0, sizeof(double) * (size_t)n * n));
+            CK(cudaMemcpy2D(A, sizeof(double) * (n + 1), diag.data(), sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice));
             cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
             cudaEventRecord(e0);
-            cusolverDnDpotrf(sh, CUBLAS_FILL_MODE_LOWER, n, A, n, work, lwork, info);
+            cusolverDnXpotrf(sh, params, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A, n, CUDA_R_64F, work, wdev, hwork.data(), whost, info);
             cudaEventRecord(e1); cudaEventSynchronize(e1);
             float ms; cudaEventElapsedTime(&ms, e0, e1);
             if (ms < best) best = ms;
         }
-        printf(", \"cusolver_dpotrf_%d_tflops\": %.3f, \"cusolver_dpotrf_%d_ms\": %.2f", n, (double)n * n * n / 3.0 / best * 1e-9, n, best);
+        printf(", \"cusolver_dpotrf_%lld_tflops\": %.3f, \"cusolver_dpotrf_%lld_ms\": %.2f", (long long)n, (double)n * n * n / 3.0 / best * 1e-9, (long long)n, best);
         cudaFree(A); cudaFree(work); cudaFree(info);
     }
     printf("}\n");

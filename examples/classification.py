@@ -66,20 +66,15 @@ def main(argv=None):
         return calculate_metrics(y_test, dist)
 
     before = evaluate(1.2, "Before optimization")                               # classification.py:415
-    if args.method == "Laplace":
-        vg = classifier.value_and_grad()
+    vg = classifier.value_and_grad()       # LaplaceGP: closed-form gradient; VBGP: central differences of the ELBO
 
-        def fun(phi):                                                           # varz optimises log(lengthscale)
-            ls = float(np.exp(phi[0]))
-            value, (g_prior, _) = vg((ls, (noise_std, cutpoints)))
-            return value, np.array([g_prior * ls])
+    def fun(phi):                                                               # varz optimises log(lengthscale)
+        ls = float(np.exp(phi[0]))
+        value, (g_prior, _) = vg((ls, (noise_std, cutpoints)))
+        return value, np.array([g_prior * ls])
 
-        res = minimize(fun, np.log([1.2]), jac=True, method="L-BFGS-B")
-        ls_opt = float(np.exp(res.x[0]))
-    else:
-        obj = classifier.objective()
-        res = minimize(lambda phi: obj((float(np.exp(phi[0])), (noise_std, cutpoints))), np.log([1.2]), method="L-BFGS-B")
-        ls_opt = float(np.exp(res.x[0]))
+    res = minimize(fun, np.log([1.2]), jac=True, method="L-BFGS-B")
+    ls_opt = float(np.exp(res.x[0]))
     after = evaluate(ls_opt, "After optimization")
     return before, after, res
 

@@ -219,13 +219,14 @@ int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int3
  * (Rasmussen & Williams Alg. 5.1 / §5.5.1) of what JAX's reverse pass through fixed_point_layer returns
  * (probit/implicit/solvers.py:28-64, probit/approximators.py:132-134).  Call right after
  * pb_laplace_fit(final_factor = 1): the workspace must hold K and the factor of B(w*); the factor is
- * consumed.  grad_host[0..2] = d/dscale, d/dstretch_out, d/dsigma (NaN unless the likelihood is Gaussian;
- * ordinal sigma / cutpoint derivatives are not implemented — the reference's examples keep them fixed).
+ * consumed.  grad_host[0..2] = d/dscale, d/dstretch_out, d/dsigma; for the ordinal likelihood, when
+ * grad_len >= 3 + J + 1, grad_host[3 + j] = d/db_j (0 for the infinite end cutpoints), otherwise the
+ * ordinal sigma slot is NaN.
  * Cost: one N x N triangular inverse + U U^T (both DMMA GEMMs) + two passes over K.                  */
 int64_t pb_gradient_scratch_bytes(int64_t n);
 int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                         const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
-                        double* grad_host);
+                        double* grad_host, int32_t grad_len);
 
 /* ---- A10: predict -----------------------------------------------------------------------------
  * Approximator.predict (approximators.py:154-180): mean = K_*f w,

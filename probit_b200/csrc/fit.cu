@@ -15,6 +15,7 @@
 #include "likelihood.cuh"
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 namespace pb {
 
@@ -298,14 +299,15 @@ pcg_dir_kernel(const double* __restrict__ sc_new, const double* __restrict__ sc_
 // s2_i = 1/2 V_i d3_i with V_i = (1 - Binv_ii) / W_i = diag((K^-1 + W)^-1);
 // partials: [0] Gaussian d(-Psi)/dsigma terms  sum(-1/sigma + (y-f)^2/sigma^3 + V_i/sigma^3), [1] #(W_i <= 0)
 __global__ void __launch_bounds__(256)
-grad_s2_kernel(const double* __restrict__ Binv, int64_t ldb, const double* __restrict__ W, const double* __restrict__ d3,
+grad_s2_kernel(const double* __restrict__ neg_binv_diag, const double* __restrict__ W, const double* __restrict__ d3,
                const double* __restrict__ f, const void* __restrict__ y, int gaussian, double sigma, int64_t n,
-               double* __restrict__ s2, double* __restrict__ partial) {
+               double* __restrict__ s2, double* __restrict__ Vout, double* __restrict__ partial) {
     double acc = 0, bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double w = W[i];
         if (!(w > 0.0)) bad += 1.0;
-        const double V = (1.0 - Binv[i * ldb + i]) / w;
+        const double V = (1.0 + neg_binv_diag[i]) / w;       // neg_binv_diag = -sum_k U_ik^2 = -(B^-1)_ii
+        Vout[i] = V;
         s2[i] = 0.5 * V * d3[i];
         if (gaussian) {
             const double r = reinterpret_cast<const double*>(y)[i] - f[i];
@@ -313,6 +315,57 @@ grad_s2_kernel(const double* __restrict__ Binv, int64_t ldb, const double* __res
         }
     }
     write_partials(acc, bad, partial);
+}
+
+// Ordinal-probit likelihood parameters (oracle/gradients.py ordinal_parameter_partials): per datum
+//   t = dll/dphi + 1/2 V dh/dphi + uvec dg/dphi   for phi = sigma, the lower and the upper cutpoint,
+// accumulated per block in shared memory: slot 0 = sigma, slot 1 + j = cutpoint b_j.  partial[block][J + 2].
+__global__ void __launch_bounds__(256)
+ordinal_param_grad_kernel(const double* __restrict__ f, const long long* __restrict__ y, const double* __restrict__ cut,
+                          int J, double sigma, double eps, const double* __restrict__ V, const double* __restrict__ uvec,
+                          int64_t n, double* __restrict__ partial) {
+    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double acc[lik::MAX_CUT + 2];
+    for (int i = threadIdx.x; i <= J; i += 256) sc[i] = cut[i];
+    for (int i = threadIdx.x; i < J + 2; i += 256) acc[i] = 0.0;
+    __syncthreads();
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        long long yi = y[i];
+        yi = yi < 0 ? 0 : (yi >= J ? J - 1 : yi);
+        const double b1 = sc[yi], b2 = sc[yi + 1], fi = f[i];
+        const bool fin1 = b1 != -INFINITY, fin2 = b2 != INFINITY;
+        const double z1 = fin1 ? (b1 - fi) / sigma : 0.0, z2 = fin2 ? (b2 - fi) / sigma : 0.0;
+        const double u = ((fin2 ? lik::norm_cdf(z2) : 1.0) - (fin1 ? lik::norm_cdf(z1) : 0.0)) + eps;
+        const double A = (fin1 ? lik::norm_z_pdf(z1) : 0.0) / u, B = (fin2 ? lik::norm_z_pdf(z2) : 0.0) / u;
+        const double L1 = -A, L2 = B;
+        const double L11 = z1 * A - A * A, L12 = A * B, L22 = -z2 * B - B * B;
+        const double L111 = A * (1.0 - z1 * z1) + 3.0 * z1 * A * A - 2.0 * A * A * A;
+        const double L112 = -z1 * A * B + 2.0 * A * A * B;
+        const double L122 = -2.0 * A * B * B - z2 * A * B;
+        const double L222 = B * (z2 * z2 - 1.0) + 3.0 * z2 * B * B + 2.0 * B * B * B;
+        const double S = L11 + 2.0 * L12 + L22;
+        const double s1 = 1.0 / sigma, s2i = s1 * s1, s3i = s2i * s1;
+        const double hv = 0.5 * V[i], uv = uvec[i];
+        const double t_sigma = -(z1 * L1 + z2 * L2) * s1
+                               + hv * (-(2.0 * S + z1 * (L111 + 2.0 * L112 + L122) + z2 * (L112 + 2.0 * L122 + L222)) * s3i)
+                               + uv * (((L1 + L2) + z1 * (L11 + L12) + z2 * (L12 + L22)) * s2i);
+        const double t_lower = L1 * s1 + hv * ((L111 + 2.0 * L112 + L122) * s3i) + uv * (-(L11 + L12) * s2i);
+        const double t_upper = L2 * s1 + hv * ((L112 + 2.0 * L122 + L222) * s3i) + uv * (-(L12 + L22) * s2i);
+        atomicAdd(&acc[0], t_sigma);
+        if (fin1) atomicAdd(&acc[1 + yi], t_lower);
+        if (fin2) atomicAdd(&acc[2 + yi], t_upper);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < J + 2; i += 256) partial[(int64_t)blockIdx.x * (J + 2) + i] = acc[i];
+}
+
+__global__ void __launch_bounds__(256)
+sum_columns_kernel(const double* __restrict__ partial, int nblk, int width, double* __restrict__ out) {
+    for (int c = threadIdx.x; c < width; c += 256) {
+        double a = 0.0;
+        for (int b = 0; b < nblk; ++b) a += partial[(int64_t)b * width + c];
+        out[c] = a;
+    }
 }
 
 // out = a - b
@@ -756,11 +809,11 @@ extern "C" int64_t pb_gradient_scratch_bytes(int64_t n) {
 
 extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                                    const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
-                                   double* grad_host) {
+                                   double* grad_host, int32_t grad_len) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
-    PB_CHECK(weight && precision && grad_host, PB_ERR_INVALID, "laplace_gradient: null argument");
+    PB_CHECK(weight && precision && grad_host && grad_len >= 3, PB_ERR_INVALID, "laplace_gradient: bad argument");
     PB_CHECK(scratch && scratch_bytes >= pb_gradient_scratch_bytes(prob->n), PB_ERR_INVALID, "laplace_gradient: scratch too small");
     PB_CHECK((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, PB_ERR_INVALID, "laplace_gradient: scratch must be 256-byte aligned");
     lik::Params lp;
@@ -792,14 +845,22 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     };
     PB_TRY(s3(ws.vec(V_B), ws.vec(V_R)));       // s3_c * c
     PB_TRY(s3(ws.vec(V_T), ws.vec(V_Z)));       // s3_l * l
-    // U = L^-T (upper) in scratch, then B^-1 = U U^T (lower) over the factor
+    // U = L^-T (upper) in scratch; diag(B^-1) = row sums of squares of U -> V, s2 (the factor is still intact)
     PB_TRY(set_identity(st, U, n, ld));
     PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), U, n, ld));
-    PB_TRY(gemm_nt_mode(st, n, n, n, 1.0, U, ld, U, ld, 0.0, ws.B(), ld, 2));
-    grad_s2_kernel<<<nb, 256, 0, st>>>(ws.B(), ld, precision, d3, f, prob->y, gaussian ? 1 : 0, prob->lik.sigma, n,
-                                       ws.vec(V_P), ws.partial()); pb::note_launch();
+    row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(n, 8), 256, 0, st>>>(U, n, n, ld, 0.0, ws.vec(V_Q)); pb::note_launch();
+    grad_s2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_Q), precision, d3, f, prob->y, gaussian ? 1 : 0, prob->lik.sigma, n,
+                                       ws.vec(V_P), ws.vec(V_E), ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, sc + S_GSIG, sc + S_BAD));
+    const bool ordinal_params = !gaussian && grad_len >= 3 + prob->lik.J + 1;
+    if (ordinal_params) {
+        // uvec = (K^-1 + W)^-1 s2 = K s2 - K R K s2 (needs the Cholesky factor: do it before B^-1 overwrites it)
+        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_P), ws.vec(V_W)));
+        PB_TRY(s3(ws.vec(V_W), ws.vec(V_WN)));
+    }
+    // B^-1 = U U^T (lower) over the factor
+    PB_TRY(gemm_nt_mode(st, n, n, n, 1.0, U, ld, U, ld, 0.0, ws.B(), ld, 2));
     // lower-triangle sums (partials reuse the scratch: U is no longer needed)
     PB_TRY(gram_deriv_dots(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, ws.B(), ld, weight, sv, U, sc + S_G0));
     dot2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_P), ws.vec(V_R), ws.vec(V_P), ws.vec(V_Z), n, ws.partial()); pb::note_launch();
@@ -820,6 +881,19 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     grad_host[0] = -dZ_c;
     grad_host[1] = -dZ_l;
     grad_host[2] = gaussian ? -host[S_GSIG] : NAN;
+    if (ordinal_params) {
+        const int J = prob->lik.J, width = J + 2;
+        double* part = U;                                    // scratch is free again
+        ordinal_param_grad_kernel<<<nb, 256, 0, st>>>(f, reinterpret_cast<const long long*>(prob->y), prob->lik.cutpoints, J,
+                                                      prob->lik.sigma, prob->lik.eps, ws.vec(V_E), ws.vec(V_WN), n, part); pb::note_launch();
+        sum_columns_kernel<<<1, 256, 0, st>>>(part, (int)nb, width, part + (int64_t)nb * width); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        std::vector<double> hostp(width);
+        PB_CUDA(cudaMemcpyAsync(hostp.data(), part + (int64_t)nb * width, width * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(cudaStreamSynchronize(st));
+        grad_host[2] = -hostp[0];
+        for (int j = 0; j <= J; ++j) grad_host[3 + j] = -hostp[1 + j];     // b_0 and b_J are infinite: their slots stay 0
+    }
     return PB_OK;
 }
 

@@ -204,7 +204,9 @@ def test_value_and_grad_matches_oracle_gradient():
     assert abs(value - o.objective()((th, lik))) < TOL * abs(value)
     assert abs(g_prior[0] - G["stretch_out"]) < 1e-7 * max(1.0, abs(G["stretch_out"]))
     assert abs(g_prior[1] - G["scale"]) < 1e-7 * max(1.0, abs(G["scale"]))
-    assert g_lik == (None, None)
+    assert abs(g_lik[0] - G["sigma"]) < 1e-7 * max(1.0, abs(G["sigma"]))
+    assert np.abs(g_lik[1].numpy() - G["cutpoints"]).max() < 1e-7 * max(1.0, np.abs(G["cutpoints"]).max())
+    assert g_lik[1][0] == 0 and g_lik[1][-1] == 0
     # a bare-scalar prior parameter (examples/classification.py:414-417): d/dl only
     p2 = PA.LaplaceGP((X, y), lambda l: 1.4 * PK.Matern12().stretch(l), PU.log_probit_likelihood, tolerance=1e-9)
     v2, (g2, _) = p2.value_and_grad()((0.8, lik))

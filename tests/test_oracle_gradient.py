@@ -46,3 +46,27 @@ def test_gaussian_periodic_gradient_matches_finite_differences():
     assert abs(G["stretch_out"] - _fd(lambda t: obj(t, c, s), l)) < 1e-6 * abs(G["stretch_out"])
     assert abs(G["scale"] - _fd(lambda t: obj(l, t, s), c)) < 1e-6 * abs(G["scale"])
     assert abs(G["sigma"] - _fd(lambda t: obj(l, c, t), s)) < 1e-6 * abs(G["sigma"])
+
+
+def test_ordinal_likelihood_parameter_gradients_match_finite_differences():
+    X, y, params, _ = ordinal_problem(3, 150, 2, 4, "eq")
+    sig, cut = params[1]
+    prior = make_prior(OK, "eq_scaled")
+    th = (0.9, 1.3)
+
+    def obj(s, c):
+        gp = OA.LaplaceGP((X, y), prior, OU.log_probit_likelihood, tolerance=1e-10)
+        return gp.objective(jitter=0.0)((th, (s, c)))
+
+    gp = OA.LaplaceGP((X, y), prior, OU.log_probit_likelihood, tolerance=1e-10)
+    w = gp.weight((th, (sig, cut)))
+    G = OG.laplace_gradient(prior(th)(X), X, y, w, (sig, cut),
+                            dict(base="eq", periodic=0, scale=1.3, stretch_in=1.0, period=1.0, stretch_out=0.9), False)
+    assert abs(G["sigma"] - _fd(lambda t: obj(t, cut), sig)) < 1e-6 * abs(G["sigma"])
+    for j in range(1, 4):
+        def shifted(t, j=j):
+            c = cut.copy()
+            c[j] = t
+            return obj(sig, c)
+        assert abs(G["cutpoints"][j] - _fd(shifted, cut[j])) < 1e-6 * max(1.0, abs(G["cutpoints"][j]))
+    assert G["cutpoints"][0] == 0 and G["cutpoints"][-1] == 0

@@ -171,11 +171,21 @@ def test_block_cyclic_factorization_hook_single_gpu():
     w_ref, p_ref = o.approximate_posterior(params)
     Xs = np.random.default_rng(2).uniform(-0.5, 1.5, size=(90, 4))
     m_ref, v_ref = o.predict(Xs, params, w_ref, p_ref)
+    from probit_b200 import _lib
     with DistributedFactorization(p, nb=128) as hook:
         w, prec = p.approximate_posterior(params)
         m, v = p.predict(Xs, params, w, prec)
         obj = p.objective()(params)
         assert hook.error is None and hook.calls >= 3
+        # the stale-factor PCG policy on top of an externally produced factor (rebuilt solve workspace)
+        _lib.set_option("laplace_pcg_min_n", 0)
+        try:
+            calls = hook.calls
+            w_pcg, _ = p.approximate_posterior(params)
+            assert hook.calls == calls + 1 and p.last_result.pcg_iterations > 0
+        finally:
+            _lib.set_option("laplace_pcg_min_n", 24576)
+        assert relerr(w_pcg.cpu().numpy(), w_ref) < TOL
     assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
     assert relerr(m.cpu().numpy(), m_ref) < TOL and relerr(v.cpu().numpy(), v_ref) < TOL
     assert abs(obj - o.objective()(params)) < TOL * abs(obj)

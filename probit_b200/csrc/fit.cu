@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256)
 laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
                     const void* __restrict__ y, int64_t n, double* __restrict__ s, double* __restrict__ b,
                     double* __restrict__ partial) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256)
 posterior_stats_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
                        const void* __restrict__ y, const double* __restrict__ w, int64_t n, double* __restrict__ prec,
                        double* __restrict__ partial) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, ftw = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -143,7 +143,7 @@ posterior_stats_kernel(lik::Params p, const double* __restrict__ cut, const doub
 __global__ void __launch_bounds__(256)
 vb_rhs_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f, const void* __restrict__ y,
               int64_t n, double* __restrict__ r) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double fi = f[i];
@@ -324,9 +324,11 @@ __global__ void __launch_bounds__(256)
 ordinal_param_grad_kernel(const double* __restrict__ f, const long long* __restrict__ y, const double* __restrict__ cut,
                           int J, double sigma, double eps, const double* __restrict__ V, const double* __restrict__ uvec,
                           int64_t n, double* __restrict__ partial) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     __shared__ double acc[lik::MAX_CUT + 2];
     for (int i = threadIdx.x; i <= J; i += 256) sc[i] = cut[i];
+    for (int i = threadIdx.x; i < lik::NCDF_DOUBLES; i += 256) sc[lik::MAX_CUT + 1 + i] = lik::NCDF_TABLE[i];
+    const double* tbl = sc + lik::MAX_CUT + 1;
     for (int i = threadIdx.x; i < J + 2; i += 256) acc[i] = 0.0;
     __syncthreads();
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -335,7 +337,7 @@ ordinal_param_grad_kernel(const double* __restrict__ f, const long long* __restr
         const double b1 = sc[yi], b2 = sc[yi + 1], fi = f[i];
         const bool fin1 = b1 != -INFINITY, fin2 = b2 != INFINITY;
         const double z1 = fin1 ? (b1 - fi) / sigma : 0.0, z2 = fin2 ? (b2 - fi) / sigma : 0.0;
-        const double u = ((fin2 ? lik::norm_cdf(z2) : 1.0) - (fin1 ? lik::norm_cdf(z1) : 0.0)) + eps;
+        const double u = ((fin2 ? lik::norm_cdf(z2, tbl) : 1.0) - (fin1 ? lik::norm_cdf(z1, tbl) : 0.0)) + eps;
         const double A = (fin1 ? lik::norm_z_pdf(z1) : 0.0) / u, B = (fin2 ? lik::norm_z_pdf(z2) : 0.0) / u;
         const double L1 = -A, L2 = B;
         const double L11 = z1 * A - A * A, L12 = A * B, L22 = -z2 * B - B * B;

@@ -42,35 +42,6 @@ features_kernel(const double* __restrict__ X, int64_t n, int D, int64_t ldx, dou
     }
 }
 
-// exp(-x) for x >= 0 without the special-case handling of the library exp (the Gram kernels are issue
-// bound on FP64 transcendentals, ncu: sm__throughput 74 %, 110 instructions per element with libm exp+sqrt).
-// Cody-Waite reduction with fdlibm's ln2 split, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
-// 4e-18), exponent added directly to the high word; underflows to 0 beyond 2^-1020.  <= 2 ulp.
-__device__ __forceinline__ double exp_neg(double x) {
-    const double MAGIC = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
-    const double t = fma(-x, 1.4426950408889634, MAGIC);
-    const int n = __double2loint(t);                          // n = round(-x log2 e) <= 0
-    const double nf = t - MAGIC;
-    double r = fma(nf, -6.93147180369123816490e-01, -x);      // -x - n ln2_hi (exact product)
-    r = fma(nf, -1.90821492927058770002e-10, r);              //      - n ln2_lo
-    double p = 1.6059043836821613e-10;                        // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                      // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                     // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                     // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                    // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                      // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                     // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                     // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                     // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                    // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                    // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double res = __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
-    return n < -1020 ? 0.0 : res;
-}
-
 template <int BASE>
 __device__ __forceinline__ double base_eval_t(double scale, double r2) {
     if (BASE == PB_BASE_EQ) return scale * exp_neg(0.5 * r2);

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(256)
 likelihood_kernel(lik::Params p, const double* __restrict__ f, const void* __restrict__ yv, int64_t n, int64_t total,
                   const double* __restrict__ cut, double* __restrict__ ll, double* __restrict__ g,
                   double* __restrict__ h, double* __restrict__ d3) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t d = (total == n) ? i : i % n;
@@ -35,16 +35,18 @@ likelihood_kernel(lik::Params p, const double* __restrict__ f, const void* __res
 __global__ void __launch_bounds__(256)
 predictive_kernel(const double* __restrict__ mean, const double* __restrict__ var, int64_t n,
                   const double* __restrict__ cut, int J, double sigma, double* __restrict__ out) {
-    __shared__ double sc[lik::MAX_CUT + 1];
+    __shared__ double sc[lik::SMEM_DOUBLES];
     for (int i = threadIdx.x; i <= J; i += blockDim.x) sc[i] = cut[i];
+    for (int i = threadIdx.x; i < lik::NCDF_DOUBLES; i += blockDim.x) sc[lik::MAX_CUT + 1 + i] = lik::NCDF_TABLE[i];
     __syncthreads();
+    const double* tbl = sc + lik::MAX_CUT + 1;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double m = mean[i];
         const double s = sqrt(var[i] + sigma * sigma);
-        double lo = (sc[0] == -INFINITY) ? 0.0 : lik::norm_cdf((sc[0] - m) / s);     // utilities.py:219-221
+        double lo = (sc[0] == -INFINITY) ? 0.0 : lik::norm_cdf((sc[0] - m) / s, tbl);     // utilities.py:219-221
         for (int j = 0; j < J; ++j) {
             const double b2 = sc[j + 1];
-            const double hi = (b2 == INFINITY) ? 1.0 : lik::norm_cdf((b2 - m) / s);  // utilities.py:222-224
+            const double hi = (b2 == INFINITY) ? 1.0 : lik::norm_cdf((b2 - m) / s, tbl);  // utilities.py:222-224
             out[i * J + j] = hi - lo;
             lo = (b2 == -INFINITY) ? 0.0 : hi;
         }

@@ -2,6 +2,7 @@
 // Newton-step kernels in fit.cu.  Reference: probit/utilities.py (line cites inline).
 #pragma once
 #include "common.cuh"
+#include "ncdf_table.cuh"
 
 namespace pb {
 namespace lik {
@@ -10,12 +11,25 @@ constexpr double OVER_SQRT_2PI = 0.3989422804014327;    // utilities.py:10
 constexpr double LOG_OVER_SQRT_2PI = -0.9189385332046727; // utilities.py:11
 constexpr double SQRT2 = 1.4142135623730951;             // utilities.py:12
 
-__device__ __forceinline__ double ndtr(double z) { return 0.5 * (1.0 + erf(z / SQRT2)); }   // utilities.py:18-19
-__device__ __forceinline__ double norm_z_pdf(double z) { return OVER_SQRT_2PI * exp(-0.5 * z * z); }  // :22-23
-__device__ __forceinline__ double norm_cdf(double x) {   // utilities.py:31-34
-    if (isinf(x)) return x > 0 ? 1.0 : 0.0;
-    return ndtr(x);
+// Phi(z) - 1/2 = erf(z / sqrt 2) / 2 from the piecewise degree-12 polynomials of ncdf_table.cuh staged in shared
+// memory (tools/gen_ncdf_table.py: within ~0.5 ulp(1/2) of the exact value, tighter than a 1-ulp erf).  13 FMAs and 13 shared
+// loads instead of the ~100-instruction branchy library erf: the likelihood kernels are FP64-issue bound.
+__device__ __forceinline__ double ncdf_half(double z, const double* tbl) {
+    const double a = fabs(z);
+    if (a >= 8.5) return copysign(0.5, z);                       // |Phi - 1/2| rounds to 1/2 (also +-inf)
+    int k = (int)(a * 4.0);
+    k = k < 0 ? 0 : (k > NCDF_INTERVALS - 1 ? NCDF_INTERVALS - 1 : k);
+    const double t = a - (k + 0.5) * 0.25;
+    double p = tbl[NCDF_DEGREE * NCDF_INTERVALS + k];
+#pragma unroll
+    for (int j = NCDF_DEGREE - 1; j >= 0; --j) p = fma(p, t, tbl[j * NCDF_INTERVALS + k]);
+    p = k < NCDF_DIRECT ? p : 0.5 - p;                           // outer intervals tabulate Q = 1/2 - P
+    return z < 0.0 ? -p : p;
 }
+// utilities.py:18-19,31-34: ndtr(z) = 0.5 (1 + erf(z / sqrt 2)), with +-inf mapped to 1 / 0
+__device__ __forceinline__ double norm_cdf(double x, const double* tbl) { return 0.5 + ncdf_half(x, tbl); }
+// utilities.py:22-23; exp(-inf) = 0 for infinite z
+__device__ __forceinline__ double norm_z_pdf(double z) { return OVER_SQRT_2PI * exp_neg(0.5 * z * z); }
 __device__ __forceinline__ double series_h(double z) {   // utilities.py:37-44
     const double q = 1.0 / (z * z);
     return -q + 2.5 * q * q - (37.0 / 3.0) * q * q * q;
@@ -28,33 +42,36 @@ __device__ __forceinline__ double z_tails(double z1, double z2) { return z_far_t
 struct Out { double ll, g, h, d3; };
 
 // utilities.py:56-57 and its first three derivatives in f
-__device__ __forceinline__ Out ordinal_autodiff(double f, double b1, double b2, double sigma, double eps) {
+// (two reciprocals — 1/sigma and 1/u — replace the five divisions of the literal expression: <= 2 ulp)
+__device__ __forceinline__ Out ordinal_autodiff(double f, double b1, double b2, double sigma, double eps,
+                                                const double* tbl) {
     const bool fin1 = b1 != -INFINITY, fin2 = b2 != INFINITY;
-    const double z1 = fin1 ? (b1 - f) / sigma : 0.0;    // utilities.py:217,219-221
-    const double z2 = fin2 ? (b2 - f) / sigma : 0.0;    // utilities.py:218,222-224
-    const double cdf1 = fin1 ? norm_cdf(z1) : 0.0;
-    const double cdf2 = fin2 ? norm_cdf(z2) : 1.0;
+    const double is = 1.0 / sigma;
+    const double z1 = fin1 ? (b1 - f) * is : 0.0;       // utilities.py:217,219-221
+    const double z2 = fin2 ? (b2 - f) * is : 0.0;       // utilities.py:218,222-224
+    const double cdf1 = fin1 ? norm_cdf(z1, tbl) : 0.0;
+    const double cdf2 = fin2 ? norm_cdf(z2, tbl) : 1.0;
     const double p1 = fin1 ? norm_z_pdf(z1) : 0.0;
     const double p2 = fin2 ? norm_z_pdf(z2) : 0.0;
     const double u = (cdf2 - cdf1) + eps;               // utilities.py:225, :57
+    const double ru = 1.0 / u, r1 = is * ru, r2 = is * r1, r3 = is * r2;
     Out o;
     o.ll = log(u);
-    o.g = (p1 - p2) / (sigma * u);
-    o.h = (z1 * p1 - z2 * p2) / (sigma * sigma * u) - o.g * o.g;
-    o.d3 = ((z1 * z1 - 1.0) * p1 - (z2 * z2 - 1.0) * p2) / (sigma * sigma * sigma * u) - 3.0 * o.g * o.h -
-           o.g * o.g * o.g;
+    o.g = (p1 - p2) * r1;
+    o.h = (z1 * p1 - z2 * p2) * r2 - o.g * o.g;
+    o.d3 = ((z1 * z1 - 1.0) * p1 - (z2 * z2 - 1.0) * p2) * r3 - 3.0 * o.g * o.h - o.g * o.g * o.g;
     return o;
 }
 
 // utilities.py:88-148
 __device__ __forceinline__ void safe_Z(double f, double bt, double btp1, double sigma, double ub, double ub2,
-                                       double ub3, double& Z, double& z1s, double& z2s) {
+                                       double ub3, double& Z, double& z1s, double& z2s, const double* tbl) {
     const double SAFE = 1.0;
     const double _b = (btp1 == INFINITY) ? 0.0 : btp1;
     const double _a = (bt == -INFINITY) ? 0.0 : bt;
     z2s = (btp1 == INFINITY) ? INFINITY : (_b - f) / sigma;
     z1s = (bt == -INFINITY) ? -INFINITY : (_a - f) / sigma;
-    Z = norm_cdf(z2s) - norm_cdf(z1s);
+    Z = norm_cdf(z2s, tbl) - norm_cdf(z1s, tbl);
     double _z1s = (ub < z1s && z1s <= ub2) ? z1s : SAFE;
     const double __z2s = (ub < z1s) ? z2s : SAFE;
     double _z2s = (-ub2 <= z2s && z2s < -ub) ? z2s : SAFE;
@@ -71,10 +88,10 @@ __device__ __forceinline__ void safe_Z(double f, double bt, double btp1, double 
 
 // utilities.py:151-192; ll and d3 stay the autodiff expressions (the reference defines no safe ll)
 __device__ __forceinline__ Out ordinal_safe(double f, double b1, double b2, double sigma, double eps, double ub,
-                                            double ub2, double ub3) {
-    Out o = ordinal_autodiff(f, b1, b2, sigma, eps);
+                                            double ub2, double ub3, const double* tbl) {
+    Out o = ordinal_autodiff(f, b1, b2, sigma, eps, tbl);
     double Z, z1s, z2s;
-    safe_Z(f, b1, b2, sigma, ub, ub2, ub3, Z, z1s, z2s);
+    safe_Z(f, b1, b2, sigma, ub, ub2, ub3, Z, z1s, z2s, tbl);
     const double p1 = norm_z_pdf(z1s), p2 = norm_z_pdf(z2s);
     double E = (p1 - p2) / Z;
     E = (z1s > ub3) ? z1s : E;
@@ -101,6 +118,8 @@ __device__ __forceinline__ Out gaussian(double f, double y, double sigma) {
 
 
 constexpr int MAX_CUT = 256;
+constexpr int NCDF_DOUBLES = NCDF_INTERVALS * (NCDF_DEGREE + 1);
+constexpr int SMEM_DOUBLES = MAX_CUT + 1 + NCDF_DOUBLES;      // [cutpoints | normal-CDF table] staged per CTA
 
 struct Params {
     int kind;
@@ -124,20 +143,22 @@ inline int make_params(const pb_likelihood_spec& l, Params& p) {
     return PB_OK;
 }
 
-// Evaluate datum d: `sc` = cutpoints staged in shared memory (ordinal kinds).
+// Evaluate datum d: `sc` = [cutpoints | normal-CDF table] staged in shared memory by stage_cutpoints (SMEM_DOUBLES).
 __device__ __forceinline__ Out eval(const Params& p, double f, const void* __restrict__ yv, int64_t d,
                                     const double* sc) {
     if (p.kind == PB_LIK_GAUSSIAN) return gaussian(f, reinterpret_cast<const double*>(yv)[d], p.sigma);
     long long yi = reinterpret_cast<const long long*>(yv)[d];
     yi = yi < 0 ? 0 : (yi >= p.J ? p.J - 1 : yi);     // JAX clamps out-of-range gather indices
     const double b1 = sc[yi], b2 = sc[yi + 1];
-    return p.kind == PB_LIK_ORDINAL_PROBIT ? ordinal_autodiff(f, b1, b2, p.sigma, p.eps)
-                                           : ordinal_safe(f, b1, b2, p.sigma, p.eps, p.ub, p.ub2, p.ub3);
+    const double* tbl = sc + MAX_CUT + 1;
+    return p.kind == PB_LIK_ORDINAL_PROBIT ? ordinal_autodiff(f, b1, b2, p.sigma, p.eps, tbl)
+                                           : ordinal_safe(f, b1, b2, p.sigma, p.eps, p.ub, p.ub2, p.ub3, tbl);
 }
 
 __device__ __forceinline__ void stage_cutpoints(const Params& p, const double* __restrict__ cut, double* sc) {
     if (p.kind != PB_LIK_GAUSSIAN) {
         for (int i = threadIdx.x; i <= p.J; i += blockDim.x) sc[i] = cut[i];
+        for (int i = threadIdx.x; i < NCDF_DOUBLES; i += blockDim.x) sc[MAX_CUT + 1 + i] = NCDF_TABLE[i];
     }
     __syncthreads();
 }

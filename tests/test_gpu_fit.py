@@ -142,25 +142,34 @@ def test_full_size_properties_n65536():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("pcg_min_n", [0, 1 << 40])
-def test_newton_policies_agree(pcg_min_n):
-    """Stale-factor PCG Newton steps (forced on at small N) and factor-every-step give the oracle's iterates."""
+@pytest.mark.parametrize("policy", ["factor_every_step", "stale_factor_pcg", "nystrom_pcg", "nystrom_pcg_eq"])
+def test_newton_policies_agree(policy):
+    """The three Newton-step policies (forced on at small N) give the oracle's iterates and iteration count:
+    factor B every step / factor once then PCG on the stale factor / Nystrom-preconditioned CG, no factorisation."""
     from probit_b200 import _lib
-    X, y, params, family = ordinal_problem(11, 800, 4, 5, "matern12")
+    family = "eq" if policy.endswith("_eq") else "matern12"      # EQ: numerically rank-deficient landmark block
+    X, y, params, family = ordinal_problem(11, 1500, 4, 5, family)
     o, p = _pair(X, y, family)
     w_ref, p_ref = o.approximate_posterior(params)
-    _lib.set_option("laplace_pcg_min_n", pcg_min_n)
+    _lib.set_option("laplace_pcg_min_n", 1 << 40 if policy == "factor_every_step" else 0)
+    _lib.set_option("laplace_nystrom_rank", -1 if policy.startswith("nystrom") else 0)
     try:
         w, prec = p.approximate_posterior(params)
         res = p.last_result
+        m, v = p.predict(X[:50] + 0.01, params, w, prec)
     finally:
         _lib.set_option("laplace_pcg_min_n", 24576)
+        _lib.set_option("laplace_nystrom_rank", -1)
     assert res.iterations == len(o.trace)
     assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
-    if pcg_min_n == 0:
+    m_ref, v_ref = o.predict(X[:50] + 0.01, params, w_ref, p_ref)
+    assert relerr(m.cpu().numpy(), m_ref) < TOL and relerr(v.cpu().numpy(), v_ref) < TOL
+    if policy == "factor_every_step":
+        assert res.factorizations == res.iterations and res.pcg_iterations == 0
+    elif policy == "stale_factor_pcg":
         assert res.factorizations <= 2 and res.pcg_iterations > 0
     else:
-        assert res.factorizations == res.iterations and res.pcg_iterations == 0
+        assert res.factorizations == 0 and res.pcg_iterations > 0
 
 
 def test_block_cyclic_factorization_hook_single_gpu():
@@ -180,12 +189,14 @@ def test_block_cyclic_factorization_hook_single_gpu():
         assert hook.error is None and hook.calls >= 3
         # the stale-factor PCG policy on top of an externally produced factor (rebuilt solve workspace)
         _lib.set_option("laplace_pcg_min_n", 0)
+        _lib.set_option("laplace_nystrom_rank", 0)
         try:
             calls = hook.calls
             w_pcg, _ = p.approximate_posterior(params)
             assert hook.calls == calls + 1 and p.last_result.pcg_iterations > 0
         finally:
             _lib.set_option("laplace_pcg_min_n", 24576)
+            _lib.set_option("laplace_nystrom_rank", -1)
         assert relerr(w_pcg.cpu().numpy(), w_ref) < TOL
     assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
     assert relerr(m.cpu().numpy(), m_ref) < TOL and relerr(v.cpu().numpy(), v_ref) < TOL

@@ -296,6 +296,8 @@ def run_ours(args):
                              if cholesky_mode else
                              f"restarts: one hyperparameter restart per GPU x{world}, no data-path collective")),
             "newton_iterations": iterations, "cholesky_per_step": n_potrf, "pcg_iterations_per_step": pcg_iterations,
+            "newton_policy": ("Nystrom-preconditioned CG (no factorisation)" if fit_factorizations == 0 else
+                              "Cholesky of B, then PCG on the stale factor" if pcg_iterations else "Cholesky of B every step"),
             "l2": "inputs larger than L2 (K and the factor are 32 GiB each)",
             "data_generator": "classification.py:181-322 recipe, numpy default_rng(1); latent draw by the product's own Gram + potrf",
         },

@@ -75,9 +75,10 @@ typedef struct pb_likelihood_spec {
 
 int pb_version(void);
 const char* pb_last_error(void);
-/* Tunables: "laplace_pcg_min_n" (smallest N at which late Newton steps use stale-factor PCG instead of a
- * fresh factorisation; default 24576, 0 = always, huge = never), "potrf_block" (panel width, 0 = auto),
- * "potrf_lookahead" (0/1). */
+/* Tunables: "laplace_pcg_min_n" (smallest N at which Newton steps are solved by preconditioned CG instead of a
+ * fresh factorisation; default 24576, 0 = always, huge = never), "laplace_nystrom_rank" (landmarks of the
+ * Nystrom CG preconditioner: -1 = auto = n/16 clamped to [256, 4096], 0 = off, i.e. factor once and reuse the
+ * stale factor as the preconditioner), "potrf_block" (panel width, 0 = auto), "potrf_lookahead" (0/1). */
 int pb_set_option(const char* name, double value);
 
 /* Measurement hooks used by bench.py: total kernel launches issued by this library so far, and
@@ -163,9 +164,11 @@ int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl
  * pb_laplace_fit: LaplaceGP.weight + precision (approximators.py:204-210,265-277) = Newton on
  *   g(Kw) - w = 0 with jaxopt's stopping rule (solvers.py:7-25): w0 = 0; repeat w+ = Newton(w);
  *   err = ||w+ - w||_2; until err <= tol or iters == maxiter.  Synchronises `stream` once per
- *   iteration (8-byte readback of err).  The first two Newton steps factor B = I + W^1/2 K W^1/2; later
- *   steps solve with PCG preconditioned by the last factor when n >= "laplace_pcg_min_n" (refactoring if
- *   PCG stalls).  Outputs: weight w (n), precision p = -h(Kw) (n),
+ *   iteration (8-byte readback of err).  Each step solves with B = I + W^1/2 K W^1/2.  Below
+ *   "laplace_pcg_min_n" B is factored every step.  Above it the solve is CG to a relative residual of
+ *   1e-13, preconditioned by a rank-r Nystrom approximation of K rebuilt for the step's W (no N^3 work);
+ *   should that stall, B is factored once and later steps run PCG on the stale factor (refactoring if
+ *   that stalls too).  pb_fit_result.factorizations / pcg_iterations report what happened.  Outputs: weight w (n), precision p = -h(Kw) (n),
  *   posterior mean f = K w (n); when `final_factor` != 0 the workspace additionally ends holding
  *   the Cholesky factor of B(w*) used by pb_laplace_objective / pb_predict.
  * pb_vb_fit: VBGP.weight + precision (approximators.py:332-339; VB.py:4-16).                     */

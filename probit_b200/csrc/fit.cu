@@ -752,8 +752,10 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         } else if (nystrom_live && !have_factor) {
             int used = -1;
             bool ok = false;
-            // delta regularises a numerically rank-deficient landmark block (EQ kernels); M stays SPD for any delta
-            PB_TRY(nystrom_build(st, ws, ny, n, ws.vec(V_S), 1e-8 * prob->kernel.scale, &ok));
+            // delta regularises a numerically rank-deficient landmark block (EQ kernels: cond(K_II) > 1e16).  M is
+            // SPD for any delta >= 0; delta perturbs the approximated K by ~(n/r) delta, i.e. the preconditioned
+            // spectrum by (n/r) delta W ~ 0.04, while keeping cond(A) <~ 1e8.
+            PB_TRY(nystrom_build(st, ws, ny, n, ws.vec(V_S), 1e-3 * prob->kernel.scale, &ok));
             if (ok) PB_TRY(nystrom_pcg(st, ws, ny, n, ws.vec(V_S), ws.vec(V_C), 150, 1e-13, nystrom_warm, &used));
             if (used >= 0) {
                 solved = true;

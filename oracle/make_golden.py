@@ -28,6 +28,13 @@ CASES = {
     "c4_small_ordinal_j5_n250": dict(kind="ordinal", seed=4, N=250, D=4, J=5, family="matern12", lengthscale=1.0,
                                      cls="LaplaceGP"),
     "vb_ordinal_j3_n120": dict(kind="ordinal", seed=7, N=120, D=2, J=3, family="eq", lengthscale=0.8, cls="VBGP"),
+    # binary classification (J=2: both cutpoint intervals are half-infinite), D=2
+    "binary_j2_n80": dict(kind="ordinal", seed=12, N=80, D=2, J=2, family="matern12", lengthscale=0.7, cls="LaplaceGP"),
+    # VBGP with the Gaussian likelihood (regression through the variational path)
+    "vb_regression_n40": dict(kind="regression", seed=3, N=40, cls="VBGP"),
+    # the reference's optional "safe" derivative functions passed explicitly (examples/classification.py:406-407)
+    "safe_ordinal_j3_n30": dict(kind="ordinal", seed=1, N=30, D=1, J=3, family="eq", lengthscale=1.2, cls="LaplaceGP",
+                                safe=True),
 }
 
 
@@ -42,15 +49,17 @@ def build(case):
         gaussian = False
         n_test, D = 64, case["D"]
     Xs = np.random.default_rng(case["seed"] + 100).uniform(-0.5, 1.5, size=(n_test, D))
+    extra = dict(grad_log_likelihood=OU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=OU.hessian_log_probit_likelihood) if case.get("safe") else {}
     gp = getattr(OA, case["cls"])((X, y), make_prior(OK, family),
-                                  OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood)
+                                  OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood, **extra)
     w, p = gp.approximate_posterior(params)
     iters = len(gp.trace)
     m, v = gp.predict(Xs, params, w, p)
     obj = gp.objective()(params)
     out = dict(X=X, y=y, Xs=Xs, weight=w, precision=p, mean=m, variance=v, objective=np.array(obj),
                iterations=np.array(iters), family=np.array(family), gaussian=np.array(gaussian),
-               cls=np.array(case["cls"]), sigma=np.array(params[1][0]))
+               cls=np.array(case["cls"]), sigma=np.array(params[1][0]), safe=np.array(bool(case.get("safe"))))
     if gaussian:
         out["theta"] = np.array(params[0])
     else:
@@ -63,5 +72,7 @@ def build(case):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     for name, case in CASES.items():
+        if os.path.exists(os.path.join(OUT, name + ".npz")) and "--all" not in sys.argv:
+            continue                       # frozen fixtures are not rewritten unless asked
         np.savez(os.path.join(OUT, name + ".npz"), **build(case))
         print("wrote", name)

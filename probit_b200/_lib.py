@@ -74,6 +74,8 @@ SIGNATURES = {
     "pb_set_factor_callback": (_i32, [_p, _p]),
     "pb_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _f64, _p, _i64, _i32]),
     "pb_symv": (_i32, [_p, _p, _i64, _i64, _p, _p]),
+    "pb_symv_lower_scratch_bytes": (_i64, [_i64]),
+    "pb_symv_lower": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _i64]),
     "pb_trsv": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _p]),
     "pb_logdet_chol": (_i32, [_p, _p, _i64, _i64, _p]),
     "pb_trsm_right_lt": (_i32, [_p, _p, _i64, _i64, _p, _p, _i64, _i64]),

@@ -155,6 +155,8 @@ int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, 
 
 // blas2.cu
 int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y);
+int64_t symv_lower_scratch_doubles(int64_t n);
+int symv_lower(cudaStream_t stream, const double* K, int64_t n, int64_t ld, const double* x, double* y, double* scratch);
 int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const double* dinv, bool trans, double* rhs,
          double* x);
 int logdet_chol(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* out);

@@ -488,16 +488,19 @@ int factor_B(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double j
 // iteration (readback of the residual norm).
 template <class Precond>
 int pcg_run(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const double* c, int maxit, double tol,
-            bool warm, int* iters, Precond&& precondition) {
+            bool warm, int* iters, Precond&& precondition, double* symv_scratch = nullptr) {
     const unsigned nb = vec_blocks(n);
     const int64_t ld = ws.L.ld;
+    auto Kmul = [&](const double* in, double* out) -> int {       // half-traffic symv when scratch is available
+        return symv_scratch ? symv_lower(st, ws.K(), n, ld, in, out, symv_scratch) : gemv(st, ws.K(), n, n, ld, in, out);
+    };
     double* sc = ws.scalars();
     double host[S_COUNT];
     *iters = -1;
     if (warm) {
         // r = c - B y0: u = s o y0, t = K u, r = c - (y0 + s o t); partials: ||c||^2, ||r||^2
         pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(s, ws.vec(V_Y), nullptr, n, ws.vec(V_U), ws.partial()); pb::note_launch();
-        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_U), ws.vec(V_T)));
+        PB_TRY(Kmul(ws.vec(V_U), ws.vec(V_T)));
         pcg_warm_kernel<<<nb, 256, 0, st>>>(c, ws.vec(V_Y), s, ws.vec(V_T), n, ws.vec(V_R), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, sc + S_R0, sc + S_RR));
@@ -514,7 +517,7 @@ int pcg_run(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const dou
     PB_CUDA(cudaMemcpyAsync(ws.vec(V_P), ws.vec(V_Z), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     for (int j = 1; j <= maxit; ++j) {
         pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(s, ws.vec(V_P), nullptr, n, ws.vec(V_U), ws.partial()); pb::note_launch();
-        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_U), ws.vec(V_T)));
+        PB_TRY(Kmul(ws.vec(V_U), ws.vec(V_T)));
         pcg_bp_kernel<<<nb, 256, 0, st>>>(ws.vec(V_P), s, ws.vec(V_T), n, ws.vec(V_Q), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, sc + S_PBP, nullptr));
@@ -570,6 +573,7 @@ struct Nystrom {
     double* pws = nullptr;    // potrf workspace of A
     double* t = nullptr;      // r
     double* u = nullptr;      // r
+    double* symv = nullptr;   // scratch of the half-traffic symv (null when ld is not padded to 64)
 };
 
 int64_t nystrom_rank(int64_t n) {
@@ -592,6 +596,7 @@ Nystrom nystrom_layout(const Ws& ws, int64_t n) {
     ny.pws = take(ny.pws_bytes / 8 + 1);
     ny.t = take(ny.r);
     ny.u = take(ny.r);
+    if (ws.L.ld >= round_up(n, 64)) ny.symv = take(symv_lower_scratch_doubles(n));
     if (p - ws.B() > n * ws.L.ld) ny.r = 0;      // does not fit (tiny n): disabled
     return ny;
 }
@@ -653,7 +658,7 @@ int nystrom_pcg(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, con
         PB_CUDA(cudaGetLastError());
         return finalize(st, ws, nb, rz_slot, nullptr);
     };
-    return pcg_run(st, ws, n, s, c, maxit, tol, warm, iters, precondition);
+    return pcg_run(st, ws, n, s, c, maxit, tol, warm, iters, precondition, ny.symv);
 }
 
 bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
@@ -724,12 +729,14 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
     bool nystrom_live = ny.r > 0, nystrom_warm = false;
     while (error > tolerance && it < maxiter) {                             // jaxopt loop (solvers.py:13-14)
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
+        else if (nystrom_live && !have_factor && ny.symv) PB_TRY(symv_lower(st, ws.K(), n, ld, w, ws.vec(V_F), ny.symv));
         else PB_TRY(gemv(st, ws.K(), n, n, ld, w, ws.vec(V_F)));
         laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_S),
                                                 ws.vec(V_B), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
-        PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));       // K b
+        if (nystrom_live && !have_factor && ny.symv) PB_TRY(symv_lower(st, ws.K(), n, ld, ws.vec(V_B), ws.vec(V_T), ny.symv));
+        else PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_B), ws.vec(V_T)));  // K b
         mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C)); pb::note_launch();
         // x = B^{-1} (s o K b).  Large n: CG with the Nystrom preconditioner, no factorisation at all.  If that
         // ever stalls, or below "laplace_pcg_min_n": the first iteration factors B; later ones reuse the last

@@ -168,6 +168,22 @@ def symv(K, x):
     return y
 
 
+def symv_lower(K, x):
+    """K @ x for a symmetric K stored in full, reading only the lower triangle's tiles (half the traffic)."""
+    lib = _lib.load()
+    n = K.shape[0]
+    if _ld(K) < (n + 63) // 64 * 64:                      # the kernel reads whole 64-column tiles of the padded rows
+        Kp = torch.zeros((n, (n + 63) // 64 * 64), dtype=torch.float64, device="cuda")
+        Kp[:, :n] = K
+        K = Kp[:, :n]
+    x = _dev(x)
+    y = torch.empty_like(x)
+    nbytes = lib.pb_symv_lower_scratch_bytes(n)
+    scratch = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    _lib.check(lib.pb_symv_lower(_stream(), _ptr(K), n, _ld(K), _ptr(x), _ptr(y), _ptr(scratch), nbytes))
+    return y
+
+
 def trmv_lower(A, z):
     """L @ z for the lower triangle of A (used only by the synthetic-data generator)."""
     return torch.tril(A) @ z

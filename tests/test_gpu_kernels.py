@@ -184,6 +184,24 @@ def test_predictive_distributions_match_oracle():
     assert np.abs(P.sum(1) - 1).max() < 1e-14
 
 
+@pytest.mark.parametrize("n", [1, 2, 63, 64, 65, 127, 128, 129, 1000, 4097])
+def test_symv_lower_matches_dense_product_ragged_sizes(n):
+    """The half-traffic symmetric matvec (lower tiles only) on ragged sizes; padding columns hold NaN on purpose."""
+    torch = _torch()
+    from probit_b200 import linalg
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)); A = A + A.T
+    ld = (n + 63) // 64 * 64
+    buf = torch.full((n, ld), float("nan"), dtype=torch.float64, device="cuda")
+    buf[:, :n] = torch.as_tensor(A, device="cuda")
+    x = rng.standard_normal(n)
+    y = linalg.symv_lower(buf[:, :n], torch.as_tensor(x, device="cuda")).cpu().numpy()
+    assert np.all(np.isfinite(y))
+    assert relerr(y, A @ x) < 1e-13
+    y2 = linalg.symv_lower(buf[:, :n], torch.as_tensor(x, device="cuda")).cpu().numpy()
+    assert np.array_equal(y, y2)                      # deterministic: fixed summation order, no atomics
+
+
 def test_symv_and_trsv_large_ragged():
     torch = _torch()
     from probit_b200 import linalg

@@ -24,7 +24,7 @@ def best_ms(fn, reps=3, warm=1):
 
 
 out = {"peaks": {"hbm_gbs": HBM, "fp64_dmma_tflops": DMMA}}
-which = sys.argv[1:] or ["gram", "likelihood", "predictive", "predict", "c3"]
+which = sys.argv[1:] or ["gram", "symv", "likelihood", "predictive", "predict", "c3"]
 
 if "gram" in which:
     # write-only reference: torch fill_ over the same 32 GiB (what an ideal Gram kernel is bounded by)
@@ -46,6 +46,25 @@ if "gram" in which:
         out[f"gram_{fam}_N{n}_D{D}"] = {"ms": ms, "GBs": gbs, "frac_hbm": gbs / HBM, "algorithmic_bytes": 8.0 * n * n}
         del K, X, Z
         torch.cuda.empty_cache()
+
+if "symv" in which:
+    n = 65536
+    K = linalg.empty_matrix(n, n)
+    K.normal_()
+    x = torch.randn(n, dtype=torch.float64, device="cuda")
+    y = torch.empty_like(x)
+    lib = _lib.load()
+    import ctypes as C
+    ms = best_ms(lambda: lib.pb_symv(linalg._stream(), linalg._ptr(K), n, K.stride(0), linalg._ptr(x), linalg._ptr(y)))
+    out["symv_full_65536"] = {"ms": ms, "GBs": n * n * 8 / ms * 1e-6, "frac_hbm": n * n * 8 / ms * 1e-6 / HBM}
+    nbytes = lib.pb_symv_lower_scratch_bytes(n)
+    scratch = torch.empty(nbytes // 8, dtype=torch.float64, device="cuda")
+    ms = best_ms(lambda: lib.pb_symv_lower(linalg._stream(), linalg._ptr(K), n, K.stride(0), linalg._ptr(x), linalg._ptr(y), linalg._ptr(scratch), nbytes))
+    alg = n * (n + 64) / 2 * 8
+    out["symv_lower_65536"] = {"ms": ms, "algorithmic_bytes": alg, "GBs": alg / ms * 1e-6, "frac_hbm": alg / ms * 1e-6 / HBM,
+                               "note": "algorithmic bytes = the tiles on and below the diagonal, read once"}
+    del K, scratch
+    torch.cuda.empty_cache()
 
 if "likelihood" in which:
     n, batch, J = 65536, 1024, 5           # restarts x N = 2^26 elements

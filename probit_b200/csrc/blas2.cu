@@ -310,6 +310,45 @@ logdet_kernel(const double* __restrict__ L, int64_t n, int64_t ldl, double* __re
 }
 
 
+// ---- transposed matvec: partial[split][j] = sum_{i in split} A[i][j] x[i], A rows x cols row-major ----
+// Column-parallel (lane = 2 adjacent columns, 16-byte loads), rows cut into gridDim.y chunks so that a short, wide
+// A (the r x N Nystrom factor) still fills the machine; the caller sums the chunks in fixed order.
+constexpr int GT_ROWS = 512;        // rows per chunk staged in shared memory
+
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const double* __restrict__ A, int64_t rows, int64_t cols, int64_t lda, const double* __restrict__ x,
+              double* __restrict__ partial, int64_t ldp) {
+    __shared__ double xs[GT_ROWS];
+    const int64_t i0 = (int64_t)blockIdx.y * GT_ROWS;
+    const int cnt = (int)(rows - i0 < GT_ROWS ? rows - i0 : GT_ROWS);
+    for (int i = threadIdx.x; i < cnt; i += 256) xs[i] = x[i0 + i];
+    __syncthreads();
+    const int64_t j = (blockIdx.x * 256ll + threadIdx.x) * 2;
+    if (j >= cols) return;
+    const double* a = A + i0 * lda + j;                 // j + 1 < lda always: lda is even and >= cols
+    double s0 = 0, s1 = 0, t0 = 0, t1 = 0;
+    int i = 0;
+    for (; i + 8 <= cnt; i += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = __ldcs(reinterpret_cast<const double2*>(a + (int64_t)(i + k) * lda));
+#pragma unroll
+        for (int k = 0; k < 8; k += 2) {
+            s0 = fma(v[k].x, xs[i + k], s0);
+            s1 = fma(v[k].y, xs[i + k], s1);
+            t0 = fma(v[k + 1].x, xs[i + k + 1], t0);
+            t1 = fma(v[k + 1].y, xs[i + k + 1], t1);
+        }
+    }
+    for (; i < cnt; ++i) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>(a + (int64_t)i * lda));
+        s0 = fma(v.x, xs[i], s0);
+        s1 = fma(v.y, xs[i], s1);
+    }
+    partial[blockIdx.y * ldp + j] = s0 + t0;
+    if (j + 1 < cols) partial[blockIdx.y * ldp + j + 1] = s1 + t1;
+}
+
 // ---- symv that reads only the lower triangle's tiles: half the HBM traffic of the row-wise gemv ----
 // K is stored in full, but y = K x only needs each off-diagonal 64x64 tile once: the tile (I, J), J < I, gives
 // y_I += T x_J (kept in registers along the CTA's row strip) and y_J += T^T x_I (summed over the CTA's 64 rows and
@@ -412,6 +451,20 @@ symv_reduce_kernel(const double* __restrict__ rowpart, const double* __restrict_
 int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y) {
     if (rows == 0) return PB_OK;
     gemv_kernel<<<(unsigned)ceil_div<int64_t>(rows, 4), 256, 0, stream>>>(A, rows, cols, lda, x, y); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int gemv_t_splits(int64_t rows) { return (int)ceil_div<int64_t>(rows, GT_ROWS); }
+
+// partial[k * ldp + j], k < gemv_t_splits(rows): the caller adds the chunks.  A 16-byte aligned, lda even.
+int gemv_t_partial(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x,
+                   double* partial, int64_t ldp) {
+    if (rows == 0 || cols == 0) return PB_OK;
+    PB_CHECK((lda & 1) == 0 && lda >= cols && (reinterpret_cast<uintptr_t>(A) & 15) == 0, PB_ERR_INVALID,
+             "gemv_t: A must be 16-byte aligned with an even leading dimension");
+    dim3 grid((unsigned)ceil_div<int64_t>(ceil_div<int64_t>(cols, 2), 256), (unsigned)gemv_t_splits(rows));
+    gemv_t_kernel<<<grid, 256, 0, stream>>>(A, rows, cols, lda, x, partial, ldp); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

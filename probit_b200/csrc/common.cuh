@@ -155,6 +155,9 @@ int sym_transform(cudaStream_t stream, const double* K, int64_t n, int64_t ldk, 
 
 // blas2.cu
 int gemv(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y);
+int gemv_t_splits(int64_t rows);
+int gemv_t_partial(cudaStream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x,
+                   double* partial, int64_t ldp);
 int64_t symv_lower_scratch_doubles(int64_t n);
 int symv_lower(cudaStream_t stream, const double* K, int64_t n, int64_t ld, const double* x, double* y, double* scratch);
 int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const double* dinv, bool trans, double* rhs,

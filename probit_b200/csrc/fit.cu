@@ -557,12 +557,13 @@ int pcg_solve(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const d
 }
 
 // ---- Nystrom preconditioner: Newton steps without any N^3 factorisation ----
-// With the first r training points as landmarks I (the rows are exchangeable: X is not ordered),
+// With r landmarks I = {0, q, 2q, ...}, q = floor(n / r) (strided, so that inputs sorted along some coordinate are
+// still covered evenly),
 //     K ~ K_NI (K_II + delta I)^{-1} K_IN,      M = I + S K_NI (K_II + delta I)^{-1} K_IN S   (S = diag(s))
 //     M^{-1} = I - S K_NI A^{-1} K_IN S,        A = K_II + delta I + K_IN S^2 K_NI            (Woodbury)
-// K_NI / K_IN are the first r columns / rows of the Gram matrix already in HBM, so one application costs two
-// r x N matvecs and two r x r triangular solves (< 1 ms at N = 65536, r = 4096) beside the 5 ms symv of the CG
-// step itself.  A is rebuilt for every Newton step (one r x r x N lower GEMM on the tensor cores, 33 ms, and an
+// G = K_IN S (r x N, the landmark rows of the Gram matrix already in HBM, scaled) is kept, so one application is
+// z = r - G^T A^{-1} G r: two r x N matvecs and two r x r triangular solves (< 1 ms at N = 65536, r = 4096) beside
+// the 3 ms symv of the CG step itself.  A is rebuilt for every Newton step (one r x r x N lower GEMM on the tensor cores, 33 ms, and an
 // r x r Cholesky).  Measured on the north-star workload: ~25 CG iterations per Newton step to 1e-13, against 147+
 // unpreconditioned; EQ and long lengthscales need fewer (the kernel is closer to low rank), short lengthscales
 // need few without any help.  ws.B() is idle until the final factorisation, so everything lives there.
@@ -574,6 +575,8 @@ struct Nystrom {
     double* t = nullptr;      // r
     double* u = nullptr;      // r
     double* symv = nullptr;   // scratch of the half-traffic symv (null when ld is not padded to 64)
+    double* gt = nullptr;     // gemv_t partials: splits x ld
+    int64_t stride = 1;       // landmark i is training point i * stride
 };
 
 int64_t nystrom_rank(int64_t n) {
@@ -596,31 +599,35 @@ Nystrom nystrom_layout(const Ws& ws, int64_t n) {
     ny.pws = take(ny.pws_bytes / 8 + 1);
     ny.t = take(ny.r);
     ny.u = take(ny.r);
+    ny.gt = take(gemv_t_splits(ny.r) * ws.L.ld);
+    ny.stride = n / ny.r;
     if (ws.L.ld >= round_up(n, 64)) ny.symv = take(symv_lower_scratch_doubles(n));
     if (p - ws.B() > n * ws.L.ld) ny.r = 0;      // does not fit (tiny n): disabled
     return ny;
 }
 
-// G[i][j] = K[i][j] s[j] for the landmark rows; A[i][j] = K[i][j] + delta [i == j] for the landmark block
+// G[i][j] = K[l_i][j] s[j] for the landmark rows l_i = i * stride; A[i][j] = K[l_i][l_j] + delta [i == j]
 __global__ void __launch_bounds__(256)
 nystrom_prep_kernel(const double* __restrict__ K, int64_t ldk, const double* __restrict__ s, int64_t n, int64_t r,
-                    double delta, double* __restrict__ G, double* __restrict__ A, int64_t lda) {
+                    int64_t stride, double delta, double* __restrict__ G, double* __restrict__ A, int64_t lda) {
     const int64_t i = blockIdx.y;
+    const double* row = K + i * stride * ldk;
     for (int64_t j = blockIdx.x * 256ll + threadIdx.x; j < n; j += (int64_t)gridDim.x * 256) {
-        const double k = K[i * ldk + j];
-        G[i * ldk + j] = k * s[j];
-        if (j < r) A[i * lda + j] = k + (i == j ? delta : 0.0);
+        G[i * ldk + j] = row[j] * s[j];
+        if (j < r) A[i * lda + j] = row[j * stride] + (i == j ? delta : 0.0);
     }
 }
 
-// z = r - s o v ; partial: r.z
+// z = r - sum_k vpart[k][.] ; partial: r.z
 __global__ void __launch_bounds__(256)
-nystrom_z_kernel(const double* __restrict__ r, const double* __restrict__ s, const double* __restrict__ v, int64_t n,
+nystrom_z_kernel(const double* __restrict__ r, const double* __restrict__ vpart, int splits, int64_t ldp, int64_t n,
                  double* __restrict__ z, double* __restrict__ partial) {
     double d = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double ri = r[i];
-        const double zi = fma(-s[i], v[i], ri);
+        double v = 0.0;
+        for (int k = 0; k < splits; ++k) v += vpart[k * ldp + i];
+        const double zi = ri - v;
         z[i] = zi;
         d = fma(ri, zi, d);
     }
@@ -633,7 +640,7 @@ int nystrom_build(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, c
     int32_t* info = ws.info() + 1;
     PB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
     dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), 64), (unsigned)ny.r);
-    nystrom_prep_kernel<<<grid, 256, 0, st>>>(ws.K(), ld, s, n, ny.r, delta, ny.G, ny.A, ny.lda); pb::note_launch();
+    nystrom_prep_kernel<<<grid, 256, 0, st>>>(ws.K(), ld, s, n, ny.r, ny.stride, delta, ny.G, ny.A, ny.lda); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(gemm_nt(st, ny.r, ny.r, n, 1.0, ny.G, ld, ny.G, ld, 1.0, ny.A, ny.lda, true));
     PB_TRY(potrf(st, ny.A, ny.r, ny.lda, ny.pws, ny.pws_bytes, info));
@@ -648,13 +655,13 @@ int nystrom_pcg(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, con
                 int maxit, double tol, bool warm, int* iters) {
     const unsigned nb = vec_blocks(n);
     const int64_t ld = ws.L.ld;
-    auto precondition = [&](double* rz_slot) -> int {
-        pcg_mul_dot_kernel<<<nb, 256, 0, st>>>(s, ws.vec(V_R), nullptr, n, ws.vec(V_U), ws.partial()); pb::note_launch();
-        PB_TRY(gemv(st, ws.K(), ny.r, n, ld, ws.vec(V_U), ny.t));                    // K_IN (s o r)
+    const int splits = gemv_t_splits(ny.r);
+    auto precondition = [&](double* rz_slot) -> int {      // z = r - G^T A^{-1} G r ; rz = r.z
+        PB_TRY(gemv(st, ny.G, ny.r, n, ld, ws.vec(V_R), ny.t));
         PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, false, ny.t, ny.u));
-        PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, true, ny.u, ny.t));              // A^{-1} ...
-        PB_TRY(gemv(st, ws.K(), n, ny.r, ld, ny.t, ws.vec(V_U)));                    // K_NI ...
-        nystrom_z_kernel<<<nb, 256, 0, st>>>(ws.vec(V_R), s, ws.vec(V_U), n, ws.vec(V_Z), ws.partial()); pb::note_launch();
+        PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, true, ny.u, ny.t));
+        PB_TRY(gemv_t_partial(st, ny.G, ny.r, n, ld, ny.t, ny.gt, ld));
+        nystrom_z_kernel<<<nb, 256, 0, st>>>(ws.vec(V_R), ny.gt, splits, ld, n, ws.vec(V_Z), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         return finalize(st, ws, nb, rz_slot, nullptr);
     };

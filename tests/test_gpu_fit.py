@@ -144,13 +144,17 @@ def test_full_size_properties_n65536():
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("policy", ["factor_every_step", "stale_factor_pcg", "nystrom_pcg", "nystrom_pcg_eq"])
+@pytest.mark.parametrize("policy", ["factor_every_step", "stale_factor_pcg", "nystrom_pcg", "nystrom_pcg_eq",
+                                    "nystrom_pcg_sorted"])
 def test_newton_policies_agree(policy):
     """The three Newton-step policies (forced on at small N) give the oracle's iterates and iteration count:
     factor B every step / factor once then PCG on the stale factor / Nystrom-preconditioned CG, no factorisation."""
     from probit_b200 import _lib
     family = "eq" if policy.endswith("_eq") else "matern12"      # EQ: numerically rank-deficient landmark block
     X, y, params, family = ordinal_problem(11, 1500, 4, 5, family)
+    if policy.endswith("_sorted"):         # inputs ordered along a coordinate: the landmarks are strided, not a prefix
+        order = np.argsort(X[:, 0])
+        X, y = np.ascontiguousarray(X[order]), np.ascontiguousarray(y[order])
     o, p = _pair(X, y, family)
     w_ref, p_ref = o.approximate_posterior(params)
     _lib.set_option("laplace_pcg_min_n", 1 << 40 if policy == "factor_every_step" else 0)

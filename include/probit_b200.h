@@ -78,7 +78,8 @@ const char* pb_last_error(void);
 /* Tunables: "laplace_pcg_min_n" (smallest N at which Newton steps are solved by preconditioned CG instead of a
  * fresh factorisation; default 24576, 0 = always, huge = never), "laplace_nystrom_rank" (landmarks of the
  * Nystrom CG preconditioner: -1 = auto = n/16 clamped to [256, 4096], 0 = off, i.e. factor once and reuse the
- * stale factor as the preconditioner), "potrf_block" (panel width, 0 = auto), "potrf_lookahead" (0/1). */
+ * stale factor as the preconditioner), "laplace_cg_tol" (eta: a CG Newton solve stops once the error it leaves in
+ * the step is <= eta * tolerance, default 1e-2; floor 1e-15 relative residual), "potrf_block" (panel width, 0 = auto), "potrf_lookahead" (0/1). */
 int pb_set_option(const char* name, double value);
 
 /* Measurement hooks used by bench.py: total kernel launches issued by this library so far, and
@@ -153,6 +154,8 @@ int pb_symv(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const d
 /* The same product reading only the tiles on and below the diagonal (half the HBM traffic); needs ldk >= n rounded
  * up to 64 and pb_symv_lower_scratch_bytes(n) = ~n^2/8 bytes of scratch.  Deterministic (no atomics). */
 int64_t pb_symv_lower_scratch_bytes(int64_t n);
+/* y = A x for a general row-major A (rows x cols, leading dimension lda): one row block of the product above. */
+int pb_gemv(pb_stream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x, double* y);
 int pb_symv_lower(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x, double* y,
                   void* scratch, int64_t scratch_bytes);
 int pb_trsv(pb_stream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
@@ -170,8 +173,8 @@ int pb_trsm_right_lt(pb_stream_t stream, const double* L, int64_t n, int64_t ldl
  *   g(Kw) - w = 0 with jaxopt's stopping rule (solvers.py:7-25): w0 = 0; repeat w+ = Newton(w);
  *   err = ||w+ - w||_2; until err <= tol or iters == maxiter.  Synchronises `stream` once per
  *   iteration (8-byte readback of err).  Each step solves with B = I + W^1/2 K W^1/2.  Below
- *   "laplace_pcg_min_n" B is factored every step.  Above it the solve is CG to a relative residual of
- *   1e-13, preconditioned by a rank-r Nystrom approximation of K rebuilt for the step's W (no N^3 work);
+ *   "laplace_pcg_min_n" B is factored every step.  Above it the solve is CG until the error left in the
+ *   step is <= 1e-2 * tolerance, preconditioned by a rank-r Nystrom approximation of K rebuilt for the step's W (no N^3 work);
  *   should that stall, B is factored once and later steps run PCG on the stale factor (refactoring if
  *   that stalls too).  pb_fit_result.factorizations / pcg_iterations report what happened.  Outputs: weight w (n), precision p = -h(Kw) (n),
  *   posterior mean f = K w (n); when `final_factor` != 0 the workspace additionally ends holding
@@ -210,6 +213,12 @@ typedef int (*pb_factor_fn)(void* user, pb_stream_t stream, const double* K, int
                             double a, double jitter, double* L, int64_t ldl, void* potrf_workspace,
                             int64_t potrf_workspace_bytes, int32_t* info_dev);
 int pb_set_factor_callback(pb_factor_fn fn, void* user);
+/* Optional replacement of y = K x inside the Newton / CG iterations of pb_laplace_fit (the one O(N^2) operation of
+ * a CG step): multi-GPU jobs shard the rows of K over the ranks and all-gather y (probit_b200/distributed.py).
+ * Every rank must return the same y.  NULL restores the single-GPU kernels. */
+typedef int (*pb_matvec_fn)(void* user, pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x,
+                            double* y);
+int pb_set_matvec_callback(pb_matvec_fn fn, void* user);
 /* Build features + K(theta) into the workspace (what every fit does first); and locate K inside it. */
 int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
 /* Features of the training inputs only (all that a mean-only pb_predict with variance == NULL needs). */

@@ -47,6 +47,7 @@ class NumericError(ProbitB200Error):
 
 
 _p, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+MATVEC_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p)
 FACTOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
                         C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p)
 _SPEC, _LIK, _PROB = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER(Problem)
@@ -75,6 +76,8 @@ SIGNATURES = {
     "pb_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _f64, _p, _i64, _i32]),
     "pb_symv": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "pb_symv_lower_scratch_bytes": (_i64, [_i64]),
+    "pb_gemv": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p]),
+    "pb_set_matvec_callback": (_i32, [_p, _p]),
     "pb_symv_lower": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _i64]),
     "pb_trsv": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _p]),
     "pb_logdet_chol": (_i32, [_p, _p, _i64, _i64, _p]),

@@ -546,6 +546,12 @@ extern "C" int pb_symv(pb_stream_t stream, const double* K, int64_t n, int64_t l
     return pb::gemv(reinterpret_cast<cudaStream_t>(stream), K, n, n, ldk, x, y);
 }
 
+extern "C" int pb_gemv(pb_stream_t stream, const double* A, int64_t rows, int64_t cols, int64_t lda, const double* x,
+                       double* y) {
+    PB_CHECK(A && x && y && lda >= cols, PB_ERR_INVALID, "gemv: bad arguments");
+    return pb::gemv(reinterpret_cast<cudaStream_t>(stream), A, rows, cols, lda, x, y);
+}
+
 extern "C" int64_t pb_symv_lower_scratch_bytes(int64_t n) { return pb::symv_lower_scratch_doubles(n) * 8; }
 
 extern "C" int pb_symv_lower(pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x, double* y,

@@ -32,11 +32,13 @@ void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops) {
 // Tunables (pb_set_option); defaults chosen from measurements on B200.
 static std::atomic<long long> g_pcg_min_n{24576};     // PCG Newton steps pay off once potrf >> trsv
 static std::atomic<long long> g_nystrom_rank{-1};     // -1 = automatic (n/16 clamped to [256, 4096]), 0 = off
+static std::atomic<double> g_cg_tol{1e-2};            // CG Newton solves: error of the step <= this * Newton tolerance
 static std::atomic<int> g_potrf_nb{0};                // 0 = automatic
 static std::atomic<int> g_lookahead{1};
 
 long long opt_pcg_min_n() { return g_pcg_min_n.load(std::memory_order_relaxed); }
 long long opt_nystrom_rank() { return g_nystrom_rank.load(std::memory_order_relaxed); }
+double opt_cg_tol() { return g_cg_tol.load(std::memory_order_relaxed); }
 int opt_potrf_nb() { return g_potrf_nb.load(std::memory_order_relaxed); }
 bool opt_lookahead() { return g_lookahead.load(std::memory_order_relaxed) != 0; }
 
@@ -46,6 +48,7 @@ extern "C" int pb_set_option(const char* name, double value) {
     PB_CHECK(name != nullptr, PB_ERR_INVALID, "set_option: null name");
     if (!strcmp(name, "laplace_pcg_min_n")) pb::g_pcg_min_n.store((long long)value);
     else if (!strcmp(name, "laplace_nystrom_rank")) pb::g_nystrom_rank.store((long long)value);
+    else if (!strcmp(name, "laplace_cg_tol")) pb::g_cg_tol.store(value);
     else if (!strcmp(name, "potrf_block")) pb::g_potrf_nb.store((int)value);
     else if (!strcmp(name, "potrf_lookahead")) pb::g_lookahead.store(value != 0.0);
     else PB_CHECK(false, PB_ERR_INVALID, "set_option: unknown option '%s'", name);

@@ -22,6 +22,7 @@ void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops);
 // tunables set through pb_set_option (capi.cu)
 long long opt_pcg_min_n();
 long long opt_nystrom_rank();
+double opt_cg_tol();
 int opt_potrf_nb();
 bool opt_lookahead();
 

@@ -201,12 +201,27 @@ class DistributedFactorization:
     """Installs the block-cyclic Cholesky as the factorisation of an approximator's fit / predict drivers
     (pb_set_factor_callback).  Every rank must run the same fit on the same data (replicas)."""
 
-    def __init__(self, approximator, group=None, nb=512):
+    def __init__(self, approximator, group=None, nb=512, shard_matvec=None):
+        """shard_matvec: also replace y = K x of the Newton / CG iterations by a row-sharded product followed by an
+        all-gather (pb_set_matvec_callback); default: whenever the group has more than one rank."""
         import ctypes as C
         from . import _lib, linalg
         self.gp, self.group, self.lib, self.la = approximator, group, _lib.load(), linalg
         self.chol = BlockCyclicCholesky(approximator.N, TorchCholeskyOps(), nb=nb, group=group)
         self.calls = 0
+        self.matvec_calls = 0
+        self.shard_matvec = (self.chol.world > 1) if shard_matvec is None else bool(shard_matvec)
+        self._mv_buf = None
+
+        def matvec(user, stream, K, n, ldk, x, y):
+            try:
+                self._matvec(K, n, ldk, x, y)
+                return _lib.PB_OK
+            except Exception as exc:
+                self.error = exc
+                return _lib.PB_ERR_CUDA
+
+        self._mv_cb = _lib.MATVEC_FN(matvec)
 
         def callback(user, stream, K, n, ldk, s, a, jitter, L, ldl, pws, pws_bytes, info_dev):
             try:
@@ -222,11 +237,38 @@ class DistributedFactorization:
     def __enter__(self):
         import ctypes as C
         self.lib.pb_set_factor_callback(C.cast(self._cb, C.c_void_p), None)
+        if self.shard_matvec:
+            self.lib.pb_set_matvec_callback(C.cast(self._mv_cb, C.c_void_p), None)
         return self
 
     def __exit__(self, *exc):
         self.lib.pb_set_factor_callback(None, None)
+        self.lib.pb_set_matvec_callback(None, None)
         return False
+
+    def _matvec(self, K, n, ldk, x, y):
+        """y = K x with the rows of K split evenly over the ranks: each rank streams n/G rows (the product is HBM
+        bound, so this is the 1/G of the time) and one all-gather of 8n bytes puts the same y on every rank."""
+        import ctypes as C
+        lib, la = self.lib, self.la
+        world, rank = self.chol.world, self.chol.rank
+        chunk = -(-n // world)
+        if self._mv_buf is None or self._mv_buf.numel() != world * chunk:
+            self._mv_buf = torch.zeros(world * chunk, dtype=torch.float64, device="cuda")
+            self._mv_loc = torch.zeros(chunk, dtype=torch.float64, device="cuda")
+        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+        if hi > lo:
+            _check(lib.pb_gemv(la._stream(), C.c_void_p(K + lo * ldk * 8), hi - lo, n, ldk, C.c_void_p(x),
+                               la._ptr(self._mv_loc)))
+        if world > 1:
+            dist.all_gather_into_tensor(self._mv_buf, self._mv_loc, group=self.group)
+            full = self._mv_buf
+        else:
+            full = self._mv_loc
+        ws = self.gp._workspace()
+        off = y - ws.data_ptr()
+        ws[off: off + n * 8].view(torch.float64).copy_(full[:n])
+        self.matvec_calls += 1
 
     def _view(self, ptr, rows, ld):
         ws = self.gp._workspace()

@@ -212,6 +212,28 @@ def test_block_cyclic_factorization_hook_single_gpu():
     assert relerr(w2.cpu().numpy(), w_ref) < TOL
 
 
+def test_sharded_matvec_hook_single_gpu():
+    """The row-sharded K x of multi-GPU jobs (matvec callback -> pb_gemv on the rank's rows -> all-gather) with a world
+    of one, under the CG Newton policy: same iterates as the oracle, no factorisation, every product through the hook."""
+    from probit_b200 import _lib
+    from probit_b200.distributed import DistributedFactorization
+    X, y, params, family = ordinal_problem(13, 1500, 4, 5, "matern12")
+    o, p = _pair(X, y, family)
+    w_ref, p_ref = o.approximate_posterior(params)
+    _lib.set_option("laplace_pcg_min_n", 0)
+    try:
+        with DistributedFactorization(p, nb=128, shard_matvec=True) as hook:
+            w, prec = p.approximate_posterior(params)
+            assert hook.error is None
+            res = p.last_result
+            assert res.factorizations == 0 and hook.calls == 0
+            assert hook.matvec_calls >= res.pcg_iterations + 2 * res.iterations - 1
+    finally:
+        _lib.set_option("laplace_pcg_min_n", 24576)
+    assert res.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+
+
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
 def test_cuda_path_matches_reference_source_fixtures(path):
     """The CUDA path against tests/golden/ref_*.npz: outputs of the reference's own source files executed in the

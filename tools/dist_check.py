@@ -37,6 +37,24 @@ for n in [int(a) for a in sys.argv[1:]]:
     print(f"[rank {rank}/{world}] N={n} iterations {it1}/{gp.last_result.iterations} factorizations {f1} "
           f"single-GPU fit {t_single:.3f} s  {world}-GPU fit {t_dist:.3f} s  rel diff {err:.2e}", flush=True)
     assert err < 1e-10 and it1 == gp.last_result.iterations
+    # default Newton policy forced on (Nystrom-preconditioned CG): row-sharded K x + all-gather vs the local symv
+    _lib.set_option("laplace_pcg_min_n", 0)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    w3, _ = gp.approximate_posterior(params)
+    torch.cuda.synchronize(); t_cg_single = time.perf_counter() - t0
+    cg1 = gp.last_result.pcg_iterations
+    with DistributedFactorization(gp) as hook:
+        dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+        w4, _ = gp.approximate_posterior(params)
+        torch.cuda.synchronize(); dist.barrier(); t_cg_dist = time.perf_counter() - t0
+        assert hook.error is None, hook.error
+        mv = hook.matvec_calls
+    err_cg = ((w4 - w3).norm() / w3.norm()).item()
+    print(f"[rank {rank}/{world}] N={n} CG Newton: single {t_cg_single:.3f} s ({cg1} CG)  sharded matvec {t_cg_dist:.3f} s "
+          f"({gp.last_result.pcg_iterations} CG, {mv} sharded products)  rel diff {err_cg:.2e}  vs factor path "
+          f"{((w3 - w1).norm() / w1.norm()).item():.2e}", flush=True)
+    assert err_cg < 1e-10 and mv > 0
+    _lib.set_option("laplace_pcg_min_n", 24576)
     del gp
     torch.cuda.empty_cache()
 dist.destroy_process_group()

@@ -197,6 +197,32 @@ class TorchCholeskyOps:
         self.linalg.gemm_nt(A, B, C_out, alpha=alpha, beta=beta, lower_only=False)
 
 
+def row_shard(n, rank, world):
+    """Equal-sized (padded) row chunks for an all-gather: returns (lo, hi, chunk); ranks past the end get lo == hi."""
+    chunk = -(-n // world)
+    return min(n, rank * chunk), min(n, (rank + 1) * chunk), chunk
+
+
+def sharded_matvec(local_product, n, group=None, device=None, buffers=None):
+    """y = K x with the rows of K split over the ranks.  `local_product(lo, hi, out)` writes K[lo:hi] @ x into
+    out[:hi - lo]; one all_gather_into_tensor of 8 * chunk bytes per rank returns the same y (length n) everywhere.
+    `buffers` (dict) caches the padded send / receive tensors between calls."""
+    rank, world = _world(group)
+    lo, hi, chunk = row_shard(n, rank, world)
+    buffers = buffers if buffers is not None else {}
+    if buffers.get("chunk") != (chunk, world):
+        buffers["chunk"] = (chunk, world)
+        buffers["loc"] = torch.zeros(chunk, dtype=torch.float64, device=device)
+        buffers["full"] = torch.zeros(world * chunk, dtype=torch.float64, device=device)
+    loc, full = buffers["loc"], buffers["full"]
+    if hi > lo:
+        local_product(lo, hi, loc)
+    if world > 1:
+        dist.all_gather_into_tensor(full, loc, group=group)
+        return full[:n]
+    return loc[:n]
+
+
 class DistributedFactorization:
     """Installs the block-cyclic Cholesky as the factorisation of an approximator's fit / predict drivers
     (pb_set_factor_callback).  Every rank must run the same fit on the same data (replicas)."""
@@ -251,23 +277,16 @@ class DistributedFactorization:
         bound, so this is the 1/G of the time) and one all-gather of 8n bytes puts the same y on every rank."""
         import ctypes as C
         lib, la = self.lib, self.la
-        world, rank = self.chol.world, self.chol.rank
-        chunk = -(-n // world)
-        if self._mv_buf is None or self._mv_buf.numel() != world * chunk:
-            self._mv_buf = torch.zeros(world * chunk, dtype=torch.float64, device="cuda")
-            self._mv_loc = torch.zeros(chunk, dtype=torch.float64, device="cuda")
-        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
-        if hi > lo:
-            _check(lib.pb_gemv(la._stream(), C.c_void_p(K + lo * ldk * 8), hi - lo, n, ldk, C.c_void_p(x),
-                               la._ptr(self._mv_loc)))
-        if world > 1:
-            dist.all_gather_into_tensor(self._mv_buf, self._mv_loc, group=self.group)
-            full = self._mv_buf
-        else:
-            full = self._mv_loc
+
+        def local_product(lo, hi, out):
+            _check(lib.pb_gemv(la._stream(), C.c_void_p(K + lo * ldk * 8), hi - lo, n, ldk, C.c_void_p(x), la._ptr(out)))
+
+        if self._mv_buf is None:
+            self._mv_buf = {}
+        full = sharded_matvec(local_product, n, self.group, "cuda", self._mv_buf)
         ws = self.gp._workspace()
         off = y - ws.data_ptr()
-        ws[off: off + n * 8].view(torch.float64).copy_(full[:n])
+        ws[off: off + n * 8].view(torch.float64).copy_(full)
         self.matvec_calls += 1
 
     def _view(self, ptr, rows, ld):

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from probit_b200.distributed import predict_sharded, restart_batch
+from probit_b200.distributed import predict_sharded, restart_batch, row_shard, sharded_matvec
 
 
 def _free_port():
@@ -123,3 +123,42 @@ def test_block_cyclic_cholesky_single_process():
     chol = BlockCyclicCholesky(n, _CpuOps(), nb=nb)
     chol.factor(lambda j0, w, o: o.copy_(A[j0:, j0:j0 + w]), lambda k0, w, p: Lfull[k0:, k0:k0 + w].copy_(p))
     assert (torch.tril(Lfull) - torch.linalg.cholesky(A)).abs().max().item() < 1e-10
+
+
+def _matvec_worker(rank, world, port, n, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(5)
+        K = torch.randn(n, n, dtype=torch.float64, generator=g)
+        K = K + K.T
+        buffers, ok = {}, True
+        for trial in range(3):                                   # buffers are reused between calls
+            x = torch.randn(n, dtype=torch.float64, generator=g)
+            seen = []
+            def local_product(lo, hi, dst):
+                seen.append((lo, hi))
+                dst[: hi - lo] = K[lo:hi] @ x
+            y = sharded_matvec(local_product, n, buffers=buffers)
+            lo, hi, chunk = row_shard(n, rank, world)
+            ok = ok and seen == ([(lo, hi)] if hi > lo else []) and y.numel() == n
+            ok = ok and torch.allclose(y, K @ x, rtol=0, atol=1e-12)
+        out[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharded_matvec_world2_ragged():
+    for n in (7, 64):                                            # 7: ragged last shard
+        with mp.Manager() as mgr:
+            out = mgr.dict()
+            mp.spawn(_matvec_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
+            assert dict(out) == {0: True, 1: True}
+
+
+def test_row_shard_covers_every_row_once():
+    for n in (1, 5, 8, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [row_shard(n, r, world) for r in range(world)]
+            rows = [i for lo, hi, _ in spans for i in range(lo, hi)]
+            assert rows == list(range(n)) and len({c for _, _, c in spans}) == 1

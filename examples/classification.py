@@ -66,7 +66,7 @@ def main(argv=None):
         return calculate_metrics(y_test, dist)
 
     before = evaluate(1.2, "Before optimization")                               # classification.py:415
-    vg = classifier.value_and_grad()       # LaplaceGP: closed-form gradient; VBGP: central differences of the ELBO
+    vg = classifier.value_and_grad()       # closed-form implicit gradient on the GPU (both approximators)
 
     def fun(phi):                                                               # varz optimises log(lengthscale)
         ls = float(np.exp(phi[0]))

@@ -244,6 +244,12 @@ int64_t pb_gradient_scratch_bytes(int64_t n);
 int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                         const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
                         double* grad_host, int32_t grad_len);
+/* The same for objective_VB at the fixed point of f_VB (VBGP.value_and_grad, approximators.py:132-134,316-330;
+ * VB.py:4-40): closed form of the implicit-function gradient (oracle/gradients.py::vb_gradient).  Factors
+ * sigma^2 I + K and sigma I + W^1/2 K W^1/2 in the workspace (any factor held there is overwritten).
+ * grad_host layout as above; scratch as pb_gradient_scratch_bytes(n). */
+int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
+                   const double* weight, void* scratch, int64_t scratch_bytes, double* grad_host, int32_t grad_len);
 
 /* ---- A10: predict -----------------------------------------------------------------------------
  * Approximator.predict (approximators.py:154-180): mean = K_*f w,

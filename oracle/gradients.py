@@ -115,3 +115,54 @@ def laplace_gradient(K, X, y, w, lik, spec_fields, gaussian):
     gc[~np.isfinite(cut)] = 0.0
     out["cutpoints"] = -gc
     return out
+
+
+def vb_gradient(K, X, y, w, lik, spec_fields, gaussian):
+    """d objective_VB / d (scale, stretch_out, sigma, cutpoints) at the fixed point w of f_VB (VB.py:4-40), in
+    closed form.  The reference gets it by reverse mode through `fixed_point_layer` (solvers.py:28-64).
+
+    With M = sigma^2 I + K, f = K w, g = dll/df, W = -d2ll/df2, S = W^1/2 and the identities of DESIGN.md §3.4
+        F(theta, w) = 1/2 w^T K w - N log sigma + 1/2 log|M| - sum ll(K w)          (the two traces sum to N)
+        T(theta, w) = M^-1 (K w + sigma g(K w)),   fixed point: sigma w = g(K w)
+        dF/dw       = K (w - g) = (1 - sigma) f
+        I - dT/dw   = sigma M^-1 (sigma I + K W)
+    the total derivative is dF/dphi = F_phi + u^T (M T_phi) with
+        u = (sigma I + K W)^-1 F_w / sigma = (1 - sigma)/sigma^2 (f - K S A^-1 S f),
+        using (sigma I + K W)^-1 = 1/sigma (I - K S A^-1 S) with the SPD matrix A = sigma I + S K S,
+    and, using T = w at the fixed point,
+        kernel parameter (C = dK/dphi):  M T_phi = -sigma W C w,       F_phi = (1/2 - sigma) w^T C w + 1/2 tr(M^-1 C)
+        sigma:                           M T_phi = sigma (g_sigma - w), F_phi = -N/sigma + sigma tr(M^-1) - sum ll_sigma
+        cutpoint b:                      M T_phi = sigma g_b,           F_phi = -sum ll_b."""
+    n = K.shape[0]
+    sigma = float(lik[0])
+    f = K @ w
+    if gaussian:
+        W = -U.hessian_log_gaussian_likelihood(f, y, lik) * np.ones(n)
+    else:
+        W = -U.hessian_log_probit_likelihood_autodiff(f, y, lik)
+    s = np.sqrt(W)
+    A = sigma * np.eye(n) + s[:, None] * K * s[None, :]
+    Fw = (1.0 - sigma) * f
+    u = (Fw - K @ (s * np.linalg.solve(A, s * Fw))) / sigma**2
+    Minv = np.linalg.inv(sigma**2 * np.eye(n) + K)
+    out = {}
+    for name, C in zip(("scale", "stretch_out"), kernel_derivatives(spec_fields, X, K)):
+        Cw = C @ w
+        out[name] = (0.5 - sigma) * (w @ Cw) + 0.5 * np.sum(Minv * C) - sigma * ((W * u) @ Cw)
+    if gaussian:
+        r = np.asarray(y, dtype=np.float64) - f
+        ll_s = -1.0 / sigma + r * r / sigma**3
+        g_s = -2.0 * r / sigma**3
+        out["sigma"] = -n / sigma + sigma * np.trace(Minv) - np.sum(ll_s) + sigma * (u @ (g_s - w))
+        return out
+    parts = ordinal_parameter_partials(f, y, lik)
+    y = np.asarray(y, dtype=np.int64)
+    cut = np.asarray(lik[1], dtype=np.float64)
+    out["sigma"] = (-n / sigma + sigma * np.trace(Minv) - np.sum(parts["sigma"]["ll"])
+                    + sigma * (u @ (parts["sigma"]["g"] - w)))
+    gc = np.zeros(cut.size)
+    np.add.at(gc, y, -parts["lower"]["ll"] + sigma * u * parts["lower"]["g"])
+    np.add.at(gc, y + 1, -parts["upper"]["ll"] + sigma * u * parts["upper"]["g"])
+    gc[~np.isfinite(cut)] = 0.0
+    out["cutpoints"] = gc
+    return out

@@ -75,7 +75,7 @@ def run_case(name):
     out["ll"] = np64(gp.log_likelihood(f, y, params[1]))
     out["grad_ll"] = np64(gp.grad_log_likelihood(f, y, params[1]))
     out["hess_ll"] = np64(gp.hessian_log_likelihood(f, y, params[1]))
-    if cls == "LaplaceGP":
+    if not safe:
         # implicit-function gradient through the reference's custom VJP (solvers.py:28-64)
         value, grads = gp.value_and_grad()(params)
         out["vg_value"] = np64(value)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "pb_vb_fit": (_i32, [_p, _PROB, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult)]),
     "pb_gradient_scratch_bytes": (_i64, [_i64]),
     "pb_laplace_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _p, _i64, C.POINTER(_f64), _i32]),
+    "pb_vb_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _i64, C.POINTER(_f64), _i32]),
     "pb_predict_prepare": (_i32, [_p, _PROB, _p, _i32, _p, _i64, C.POINTER(_i32)]),
     "pb_predict_scratch_bytes": (_i64, [_i64, _i32, _i64]),
     "pb_predict_covariance": (_i32, [_p, _PROB, _p, _p, _i64, _p, _i64, _p, _i64]),

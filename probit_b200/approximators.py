@@ -300,21 +300,27 @@ def _flatten_scalars(tree):
     return [float(tree)], (lambda vals: vals[0])
 
 
-def _laplace_value_and_grad(self):
-    """LaplaceGP.value_and_grad(): negative Laplace evidence and its gradient.
+def _closed_form_value_and_grad(self):
+    """value_and_grad(): the objective (negative Laplace evidence / negative ELBO) and its gradient.
 
     Replaces jit(value_and_grad(objective)) (approximators.py:132-134), i.e. JAX's reverse pass through
     `fixed_point_layer` (implicit/solvers.py:28-64), by the closed form evaluated on the GPU
-    (pb_laplace_gradient).  The gradient w.r.t. the kernel's scale and stretch is mapped back to the user's
-    `prior_parameters` through the Jacobian of the (host-side, cheap) kernel-spec lowering, taken by central
-    differences.  Returned structure mirrors `parameters`: ((d prior parameters), (d noise_std[, d cutpoints]));
+    (pb_laplace_gradient / pb_vb_gradient; derivations in oracle/gradients.py, checked there against the
+    reference's own implicit differentiation).  The gradient w.r.t. the kernel's scale and stretch is mapped back
+    to the user's `prior_parameters` through the Jacobian of the (host-side, cheap) kernel-spec lowering, taken by
+    central differences.  Returned structure mirrors `parameters`: ((d prior parameters), (d noise_std[, d cutpoints]));
     the infinite end cutpoints get 0.  (Only the series-expansion "safe" likelihood mode has no parameter
     gradient: its sigma / cutpoint entries follow the autodiff expression.)"""
+    laplace = isinstance(self, LaplaceGP)
+
     def vg(parameters):
         prior_parameters, likelihood_parameters = parameters
         w, p, _ = self._fit(parameters, final_factor=True)
         r = self.last_result
-        value = -r.sum_ll + 0.5 * r.ftw + r.logdet
+        if laplace:
+            value = -r.sum_ll + 0.5 * r.ftw + r.logdet
+        else:
+            value = 0.5 * r.ftw - self.N * math.log(float(likelihood_parameters[0])) + r.logdet - r.sum_ll
         prob, keep = self._problem(parameters)
         ws = self._workspace()
         sbytes = self.lib.pb_gradient_scratch_bytes(self.N)
@@ -322,8 +328,12 @@ def _laplace_value_and_grad(self):
         glen = 3 + (prob.lik.J + 1 if self._kind != _lib.PB_LIK_GAUSSIAN else 0)
         g3 = (C.c_double * glen)()
         self._factor_key = None
-        _lib.check(self.lib.pb_laplace_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w), _ptr(p),
-                                                _ptr(scratch), sbytes, g3, glen))
+        if laplace:
+            _lib.check(self.lib.pb_laplace_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w), _ptr(p),
+                                                    _ptr(scratch), sbytes, g3, glen))
+        else:
+            _lib.check(self.lib.pb_vb_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w),
+                                               _ptr(scratch), sbytes, g3, glen))
         del keep, scratch
         d_scale, d_stretch, d_sigma = g3[0], g3[1], g3[2]
         flat, rebuild = _flatten_scalars(prior_parameters)
@@ -347,7 +357,7 @@ def _laplace_value_and_grad(self):
     return vg
 
 
-LaplaceGP.value_and_grad = _laplace_value_and_grad
+LaplaceGP.value_and_grad = _closed_form_value_and_grad
 
 
 class VBGP(Approximator):
@@ -398,27 +408,7 @@ class VBGP(Approximator):
         sigma = float(parameters[1][0])
         return torch.full_like(m, 1.0 / sigma**2), m
 
-    def value_and_grad(self, rel_step=1e-5):
-        """approximators.py:132-134 for VBGP: (negative ELBO, gradient w.r.t. the prior parameters).
-
-        The closed-form implicit gradient is built for LaplaceGP only; here the gradient of the (GPU-evaluated)
-        objective is taken by central differences over the scalar prior parameters — two extra fits per
-        parameter, each of which factors sigma^2 I + K once.  Likelihood-parameter entries are None."""
-        obj = self.objective()
-
-        def vg(parameters):
-            prior_parameters, likelihood_parameters = parameters
-            value = obj(parameters)
-            flat, rebuild = _flatten_scalars(prior_parameters)
-            grads = []
-            for i, t in enumerate(flat):
-                h = rel_step * max(1.0, abs(t))
-                up, dn = list(flat), list(flat)
-                up[i], dn[i] = t + h, t - h
-                grads.append((obj((rebuild(up), likelihood_parameters)) - obj((rebuild(dn), likelihood_parameters))) / (2 * h))
-            n_lik = len(likelihood_parameters) if isinstance(likelihood_parameters, (tuple, list)) else 1
-            return value, (rebuild(grads), tuple([None] * n_lik))
-        return vg
+    value_and_grad = _closed_form_value_and_grad
 
     def objective(self):
         """approximators.py:316-330 -> objective_VB (VB.py:19-40): negative ELBO.

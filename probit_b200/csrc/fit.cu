@@ -1114,6 +1114,148 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     return PB_OK;
 }
 
+// s = sqrt(-h), W = -h ; partial[1]: number of data with -h < 0 or NaN
+__global__ void __launch_bounds__(256)
+vb_curvature_kernel(const double* __restrict__ h, int64_t n, double* __restrict__ s, double* __restrict__ W,
+                    double* __restrict__ partial) {
+    double bad = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double w = -h[i];
+        if (!(w >= 0.0)) bad += 1.0;
+        W[i] = w;
+        s[i] = sqrt(w);
+    }
+    write_partials(0.0, bad, partial);
+}
+
+// u = coef (f - kt), a = W o u
+__global__ void __launch_bounds__(256)
+vb_adjoint_kernel(const double* __restrict__ f, const double* __restrict__ kt, const double* __restrict__ W, double coef,
+                  int64_t n, double* __restrict__ u, double* __restrict__ a) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double ui = coef * (f[i] - kt[i]);
+        u[i] = ui;
+        a[i] = W[i] * ui;
+    }
+}
+
+// Gaussian likelihood: partial[0] = sum_i (dll_i/dsigma - sigma u_i dg_i/dsigma), r = y - f
+__global__ void __launch_bounds__(256)
+vb_gauss_sigma_kernel(const double* __restrict__ f, const double* __restrict__ y, const double* __restrict__ u,
+                      double sigma, int64_t n, double* __restrict__ partial) {
+    const double i3 = 1.0 / (sigma * sigma * sigma);
+    double t = 0;
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+        const double r = y[i] - f[i];
+        t += (-1.0 / sigma + r * r * i3) - sigma * u[i] * (-2.0 * r * i3);
+    }
+    write_partials(t, 0.0, partial);
+}
+
+// Gradient of objective_VB (VB.py:19-40) at the fixed point of f_VB (VB.py:4-16) with respect to the kernel's scale
+// and outer stretch, the noise std and the cutpoints: what the reference obtains by reverse mode through
+// fixed_point_layer (solvers.py:28-64, approximators.py:132-134,316-330), in the closed form derived and checked in
+// oracle/gradients.py::vb_gradient:
+//     dF/dphi = F_phi + u^T (M T_phi),   u = (1 - sigma)/sigma^2 (f - K S A^-1 S f),   A = sigma I + S K S,
+//     M = sigma^2 I + K,  S = (-h)^1/2;  kernel parameter with C = dK/dphi:
+//     dF/dphi = (1/2 - sigma) w^T C w + 1/2 tr(M^-1 C) - sigma (W u)^T C w.
+// Two Cholesky factorisations (M for the traces, A for the adjoint solve), one N x N right-TRSM and one SYRK, all on
+// the DMMA GEMM.  grad_host layout as pb_laplace_gradient: [d scale, d stretch_out, d sigma, d cutpoint_0..J].
+extern "C" int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
+                              const double* weight, void* scratch, int64_t scratch_bytes, double* grad_host,
+                              int32_t grad_len) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Ws ws;
+    PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    PB_CHECK(weight && grad_host && grad_len >= 3, PB_ERR_INVALID, "vb_gradient: bad argument");
+    PB_CHECK(scratch && scratch_bytes >= pb_gradient_scratch_bytes(prob->n), PB_ERR_INVALID, "vb_gradient: scratch too small");
+    PB_CHECK((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, PB_ERR_INVALID, "vb_gradient: scratch must be 256-byte aligned");
+    lik::Params lp;
+    PB_TRY(lik::make_params(prob->lik, lp));
+    const int64_t n = prob->n, ld = ws.L.ld;
+    const int Df = feature_dim(prob->kernel, prob->D);
+    const unsigned nb = vec_blocks(n);
+    const bool gaussian = prob->lik.kind == PB_LIK_GAUSSIAN;
+    const double sigma = prob->lik.sigma;
+    double* U = reinterpret_cast<double*>(scratch);
+    double* sc = ws.scalars();
+    double *f = ws.vec(V_F), *sv = ws.vec(V_S), *Wv = ws.vec(V_Q), *ones = ws.vec(V_E), *u = ws.vec(V_P), *a = ws.vec(V_R);
+    int32_t info_host = 0;
+    double host[S_COUNT];
+
+    PB_CUDA(cudaMemsetAsync(sc, 0, S_COUNT * sizeof(double), st));
+    PB_TRY(gemv(st, ws.K(), n, n, ld, weight, f));
+    PB_TRY(likelihood(st, prob->lik, f, prob->y, n, 1, nullptr, nullptr, ws.vec(V_T), nullptr));
+    vb_curvature_kernel<<<nb, 256, 0, st>>>(ws.vec(V_T), n, sv, Wv, ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, nullptr, sc + S_BAD));
+    fill_kernel<<<nb, 256, 0, st>>>(ones, n, 1.0); pb::note_launch();
+    // M = sigma^2 I + K: U = L^-T, diag(M^-1) = row sums of squares of U, M^-1 = U U^T over the factor
+    PB_TRY(factor_matrix(st, ws, n, nullptr, sigma * sigma, 0.0));
+    PB_TRY(set_identity(st, U, n, ld));
+    PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), U, n, ld));
+    row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(n, 8), 256, 0, st>>>(U, n, n, ld, 0.0, ws.vec(V_X)); pb::note_launch();
+    dot2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_X), ones, f, weight, n, ws.partial()); pb::note_launch();    // -tr(M^-1), f.w
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_GSIG, sc + S_FTW));
+    PB_TRY(gemm_nt_mode(st, n, n, n, 1.0, U, ld, U, ld, 0.0, ws.B(), ld, 2));
+    // S_G0 = w^T (K o rho) w, S_G1 = tr(M^-1 (K o rho)), S_G2 = tr(M^-1 K)   (K o rho = l dK/dl, K = c dK/dc)
+    PB_TRY(gram_deriv_dots(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, ws.B(), ld, weight, ones, U, sc + S_G0));
+    PB_TRY(read_scalars(st, ws, host, &info_host));
+    if (info_host != 0 || host[S_BAD] > 0) {
+        set_error("vb_gradient: sigma^2 I + K is not positive definite (info %d) or %d data have negative curvature",
+                  info_host, (int)host[S_BAD]);
+        return PB_ERR_NUMERIC;
+    }
+    // A = sigma I + S K S: u = (1 - sigma)/sigma^2 (f - K S A^-1 S f), a = W o u
+    PB_TRY(factor_matrix(st, ws, n, sv, sigma, 0.0));
+    mul_kernel<<<nb, 256, 0, st>>>(sv, f, n, ws.vec(V_C)); pb::note_launch();
+    PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
+    PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
+    mul_kernel<<<nb, 256, 0, st>>>(sv, ws.vec(V_C), n, ws.vec(V_X)); pb::note_launch();
+    PB_TRY(gemv(st, ws.K(), n, n, ld, ws.vec(V_X), ws.vec(V_Y)));
+    vb_adjoint_kernel<<<nb, 256, 0, st>>>(f, ws.vec(V_Y), Wv, (1.0 - sigma) / (sigma * sigma), n, u, a); pb::note_launch();
+    PB_TRY(gram_deriv_matvec(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, weight, ws.vec(V_Z)));       // (K o rho) w
+    dot2_kernel<<<nb, 256, 0, st>>>(a, f, a, ws.vec(V_Z), n, ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_GD0, sc + S_GD1));
+    dot2_kernel<<<nb, 256, 0, st>>>(u, weight, u, weight, n, ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    PB_TRY(finalize(st, ws, nb, sc + S_RZ0, nullptr));
+    double t_sigma = 0.0;
+    const int J = prob->lik.J, width = J + 2;
+    std::vector<double> hostp(gaussian ? 1 : width, 0.0);
+    if (gaussian) {
+        vb_gauss_sigma_kernel<<<nb, 256, 0, st>>>(f, reinterpret_cast<const double*>(prob->y), u, sigma, n, ws.partial()); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(finalize(st, ws, nb, sc + S_RZ1, nullptr));
+    } else {
+        // per datum dll/dphi - sigma u dg/dphi: the Laplace kernel with V = 0 and uvec = -sigma u
+        double* part = U;
+        fill_kernel<<<nb, 256, 0, st>>>(ones, n, 0.0); pb::note_launch();
+        vb_adjoint_kernel<<<nb, 256, 0, st>>>(u, ones, ones, -sigma, n, ws.vec(V_WN), ws.vec(V_X)); pb::note_launch();  // -sigma (u - 0)
+        ordinal_param_grad_kernel<<<nb, 256, 0, st>>>(f, reinterpret_cast<const long long*>(prob->y), prob->lik.cutpoints, J,
+                                                      sigma, prob->lik.eps, ones, ws.vec(V_WN), n, part); pb::note_launch();
+        sum_columns_kernel<<<1, 256, 0, st>>>(part, (int)nb, width, part + (int64_t)nb * width); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaMemcpyAsync(hostp.data(), part + (int64_t)nb * width, width * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    PB_TRY(read_scalars(st, ws, host, &info_host));
+    if (info_host != 0) {
+        set_error("vb_gradient: sigma I + W^1/2 K W^1/2 is not positive definite (info %d)", info_host);
+        return PB_ERR_NUMERIC;
+    }
+    t_sigma = gaussian ? host[S_RZ1] : hostp[0];
+    const double c = prob->kernel.scale, l = prob->kernel.stretch_out;
+    const double tr_minv = -host[S_GSIG];
+    grad_host[0] = ((0.5 - sigma) * host[S_FTW] + 0.5 * host[S_G2] - sigma * host[S_GD0]) / c;
+    grad_host[1] = ((0.5 - sigma) * host[S_G0] + 0.5 * host[S_G1] - sigma * host[S_GD1]) / l;
+    grad_host[2] = -t_sigma - (double)n / sigma + sigma * tr_minv - sigma * host[S_RZ0];
+    if (!gaussian)
+        for (int j = 0; j <= J && 3 + j < grad_len; ++j) grad_host[3 + j] = -hostp[1 + j];
+    return PB_OK;
+}
+
 // predict_covariance (probit/approximators.py:182-197): C = K_** - K_*f (K + P^-1)^-1 K_f* for n_test points
 // = K_** - V V^T with V = (s o K_*f) L_B^-T.  Needs the factor from pb_predict_prepare.  `scratch` holds V
 // (pb_predict_scratch_bytes(n, D, n_test)); `cov` is n_test x ldc, full (both triangles) on return.

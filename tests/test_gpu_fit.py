@@ -266,8 +266,8 @@ def test_cuda_path_matches_reference_source_fixtures(path):
         assert np.abs(P - ref["predictive"]).max() < TOL            # end to end (inherits the mean/variance error)
         P = PU.probit_predictive_distributions(lik, ref["mean"], ref["variance"]).cpu().numpy()
         assert np.abs(P - ref["predictive"]).max() < 1e-14          # the kernel alone, on the reference's moments
-    if cls == "LaplaceGP" and not extra:
-        # the reference differentiates through its custom-VJP fixed-point layer (adjoint solved to tol 1e-5)
+    if not extra:
+        # both approximators: the reference differentiates through its custom-VJP fixed-point layer (adjoint solved to tol 1e-5)
         value, (g_prior, g_lik) = gp.value_and_grad()(params)
         vt = np.atleast_1d(ref["vg_theta"])
         gpr = np.atleast_1d(np.asarray(g_prior, dtype=np.float64))
@@ -376,6 +376,43 @@ def test_small_and_boundary_sizes(N, D, J, family):
     wv_ref, _ = ov.approximate_posterior(params)
     wv, _ = pv.approximate_posterior(params)
     assert pv.last_result.iterations == len(ov.trace) and relerr(wv.cpu().numpy(), wv_ref) < TOL
+
+
+def test_vb_value_and_grad_matches_oracle_gradient():
+    """VBGP.value_and_grad (pb_vb_gradient: closed-form implicit gradient of the negative ELBO) against
+    oracle/gradients.py::vb_gradient, itself pinned to finite differences and to the reference's implicit
+    differentiation (tests/test_oracle_gradient.py, tests/test_reference_golden.py)."""
+    from oracle import gradients as OG
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    X, y, params, _ = ordinal_problem(6, 300, 3, 4, "matern12")
+    lik = params[1]
+    th = (0.8, 1.4)
+    prior_o = lambda t: t[1] * OK.Matern12().stretch(t[0])
+    prior_p = lambda t: t[1] * PK.Matern12().stretch(t[0])
+    o = OA.VBGP((X, y), prior_o, OU.log_probit_likelihood, tolerance=1e-11, maxiter=5000)
+    p = PA.VBGP((X, y), prior_p, PU.log_probit_likelihood, tolerance=1e-11, maxiter=5000)
+    w_ref = o.weight((th, lik))
+    G = OG.vb_gradient(prior_o(th)(X), X, y, w_ref, lik,
+                       dict(base="exp", periodic=0, scale=th[1], stretch_in=1.0, period=1.0, stretch_out=th[0]), False)
+    value, (g_prior, g_lik) = p.value_and_grad()((th, lik))
+    assert abs(value - o.objective()((th, lik))) < TOL * abs(value)
+    assert abs(g_prior[0] - G["stretch_out"]) < 1e-7 * max(1.0, abs(G["stretch_out"]))
+    assert abs(g_prior[1] - G["scale"]) < 1e-7 * max(1.0, abs(G["scale"]))
+    assert abs(g_lik[0] - G["sigma"]) < 1e-7 * max(1.0, abs(G["sigma"]))
+    assert np.abs(g_lik[1].numpy() - G["cutpoints"]).max() < 1e-7 * max(1.0, np.abs(G["cutpoints"]).max())
+    assert g_lik[1][0] == 0 and g_lik[1][-1] == 0
+    # Gaussian likelihood through the variational path (sigma > 1/2 so that f_VB contracts)
+    Xr, yr, _, fam = regression_problem(3, 40)
+    par = ((0.3, 0.8), (0.8,))
+    og = OA.VBGP((Xr, yr), make_prior(OK, fam), OU.log_gaussian_likelihood, tolerance=1e-12, maxiter=5000)
+    wr = og.weight(par)
+    Gr = OG.vb_gradient(make_prior(OK, fam)(par[0])(Xr), Xr, yr, wr, par[1],
+                        dict(base="eq", periodic=1, scale=0.8, stretch_in=1.0, period=0.5, stretch_out=0.3), True)
+    pg = PA.VBGP((Xr, yr), make_prior(PK, fam), PU.log_gaussian_likelihood, tolerance=1e-12, maxiter=5000)
+    val, (gp_, gl_) = pg.value_and_grad()(par)
+    assert abs(gp_[0] - Gr["stretch_out"]) < 1e-7 * abs(Gr["stretch_out"])
+    assert abs(gp_[1] - Gr["scale"]) < 1e-7 * abs(Gr["scale"])
+    assert abs(gl_[0] - Gr["sigma"]) < 1e-7 * abs(Gr["sigma"])
 
 
 def test_nan_inputs_raise_numeric_error_not_garbage():

@@ -90,7 +90,9 @@ def test_likelihood_derivatives_match_reference_autodiff(name):
 SPEC = {"c1_regression_n20": lambda th: dict(base="eq", periodic=1, scale=th[1], stretch_in=1.0, period=0.5, stretch_out=th[0]),
         "c2_ordinal_j3_n30": lambda l: dict(base="eq", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
         "c4_small_ordinal_j5_n250": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
-        "binary_j2_n80": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l)}
+        "binary_j2_n80": lambda l: dict(base="exp", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
+        "vb_ordinal_j3_n120": lambda l: dict(base="eq", periodic=0, scale=1.0, stretch_in=1.0, period=1.0, stretch_out=l),
+        "vb_regression_n40": lambda th: dict(base="eq", periodic=1, scale=th[1], stretch_in=1.0, period=0.5, stretch_out=th[0])}
 
 
 @pytest.mark.parametrize("name", sorted(SPEC))
@@ -100,11 +102,13 @@ def test_closed_form_gradient_matches_reference_implicit_differentiation(name):
     adjoint is itself a fixed-point solve to tolerance 1e-5, so agreement is to ~1e-6, not to rounding."""
     fx, ref, params, gaussian = _load(name)
     y = fx["y"] if gaussian else fx["y"].astype(np.int64)
-    gp = getattr(OA, "LaplaceGP")((fx["X"], y), make_prior(OK, str(fx["family"])),
-                                  OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood, tolerance=1e-10)
+    vb = str(fx["cls"]) == "VBGP"
+    gp = getattr(OA, str(fx["cls"]))((fx["X"], y), make_prior(OK, str(fx["family"])),
+                                     OU.log_gaussian_likelihood if gaussian else OU.log_probit_likelihood,
+                                     tolerance=1e-12 if vb else 1e-10, maxiter=5000)
     w = gp.weight(params)
     K = make_prior(OK, str(fx["family"]))(params[0])(fx["X"])
-    G = OG.laplace_gradient(K, fx["X"], y, w, params[1], SPEC[name](params[0]), gaussian)
+    G = (OG.vb_gradient if vb else OG.laplace_gradient)(K, fx["X"], y, w, params[1], SPEC[name](params[0]), gaussian)
     vg_theta = np.atleast_1d(ref["vg_theta"])
     assert abs(G["stretch_out"] - vg_theta[0]) < 2e-5 * max(1.0, abs(vg_theta[0]))
     if gaussian:

@@ -436,11 +436,17 @@ symv_reduce_kernel(const double* __restrict__ rowpart, const double* __restrict_
     if (j >= n) return;
     double s0 = rowpart[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int64_t I = j / SYT + 1;
-    for (; I + 3 < nb; I += 4) {
-        s0 += P[I * ldp + j];
-        s1 += P[(I + 1) * ldp + j];
-        s2 += P[(I + 2) * ldp + j];
-        s3 += P[(I + 3) * ldp + j];
+    for (; I + 15 < nb; I += 16) {                 // 16 independent loads in flight per thread: rows of P are 8 ldp apart
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = P[(I + k) * ldp + j];
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            s0 += v[k];
+            s1 += v[k + 1];
+            s2 += v[k + 2];
+            s3 += v[k + 3];
+        }
     }
     for (; I < nb; ++I) s0 += P[I * ldp + j];
     y[j] = (s0 + s1) + (s2 + s3);

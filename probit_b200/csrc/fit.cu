@@ -518,7 +518,6 @@ int pcg_run(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const dou
         return host[S_RR] <= std::max(tol_abs * tol_abs, 1e-30 * host[S_R0]);
     };
     const unsigned nb = vec_blocks(n);
-    const int64_t ld = ws.L.ld;
     auto Kmul = [&](const double* in, double* out) -> int { return K_times(st, ws, n, in, out, symv_scratch); };
     double* sc = ws.scalars();
     double host[S_COUNT];
@@ -608,7 +607,7 @@ struct Nystrom {
 int64_t nystrom_rank(int64_t n) {
     long long r = opt_nystrom_rank();
     if (r < 0) r = std::min<long long>(4096, std::max<long long>(256, n / 16));
-    r = std::min<long long>(r, n / 4) / 256 * 256;
+    r = std::min<long long>(std::min<long long>(r, n / 4), 32768) / 256 * 256;     // grid.y of nystrom_prep_kernel
     return r;
 }
 

@@ -144,6 +144,69 @@ def test_full_size_properties_n65536():
     torch.cuda.empty_cache()
 
 
+def _synthetic_ordinal(n, seed=3, J=5):
+    """Ordinal labels from a smooth function + noise (no N^3 latent draw): inputs for the large-N tests."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(size=(n, 4))
+    f = np.sin(3 * X[:, 0]) + X[:, 1] - X[:, 2] ** 2 + 0.3 * rng.standard_normal(n)
+    order = np.argsort(f)
+    y = np.empty(n, dtype=np.int64)
+    y[order] = (np.arange(n) * J) // n
+    fs = np.sort(f)
+    cut = np.array([-np.inf] + [0.5 * (fs[(j * n) // J] + fs[(j * n) // J - 1]) for j in range(1, J)] + [np.inf])
+    return X, y, (1.0, (float(np.sqrt(0.4)), cut))
+
+
+def test_default_large_n_policy_matches_factor_every_step_n24576():
+    """N = 24576 is where the default options switch to Nystrom-preconditioned CG Newton steps on the half-traffic
+    symv; nothing is overridden here.  Reference point: the same fit with a Cholesky of B in every Newton step."""
+    from probit_b200 import _lib, approximators as PA, kernels as PK, utilities as PU
+    n = 24576
+    X, y, params = _synthetic_ordinal(n)
+    gp = PA.LaplaceGP((X, y), lambda l: 1.0 * PK.Matern12().stretch(l), PU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    res = gp.last_result
+    assert res.factorizations == 0 and res.pcg_iterations > 0
+    Xs = np.random.default_rng(1).uniform(-0.2, 1.2, size=(200, 4))
+    m, v = gp.predict(Xs, params, w, p)
+    _lib.set_option("laplace_pcg_min_n", 1 << 40)
+    try:
+        w0, p0 = gp.approximate_posterior(params)
+        res0 = gp.last_result
+        m0, v0 = gp.predict(Xs, params, w0, p0)
+    finally:
+        _lib.set_option("laplace_pcg_min_n", 24576)
+    assert res0.factorizations == res0.iterations == res.iterations
+    assert relerr(w.cpu().numpy(), w0.cpu().numpy()) < 1e-9 and relerr(p.cpu().numpy(), p0.cpu().numpy()) < 1e-9
+    assert relerr(m.cpu().numpy(), m0.cpu().numpy()) < 1e-9 and relerr(v.cpu().numpy(), v0.cpu().numpy()) < 1e-9
+
+
+def test_full_size_ordinal_fit_properties_n65536():
+    """BASELINE configs[3] size through the class API with default options: the returned weight satisfies the
+    reference's fixed-point equation w = grad_ll(K w) (Laplace.py:4-9) far inside the solver tolerance, the
+    precision is -hessian_ll(K w), and the predictive moments are consistent (0 <= var <= k**, probabilities sum to 1)."""
+    import torch
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU, _lib
+    n = 65536
+    X, y, params = _synthetic_ordinal(n, seed=5)
+    gp = PA.LaplaceGP((X, y), lambda l: 1.0 * PK.Matern12().stretch(l), PU.log_probit_likelihood)
+    w, p = gp.approximate_posterior(params)
+    res = gp.last_result
+    assert res.iterations <= 12 and res.error <= 1e-5 and res.factorizations == 0
+    prec, f = gp.precision(w, params)
+    out = PU.evaluate_likelihood(_lib.PB_LIK_ORDINAL_PROBIT, f, gp.y, params[1], ("g", "h"))
+    assert ((out["g"] - w).norm() / w.norm()).item() < 1e-8          # fixed point of f_LA
+    assert ((prec - p).norm() / p.norm()).item() < 1e-13 and ((-out["h"] - p).norm() / p.norm()).item() < 1e-13
+    assert bool((p > 0).all())
+    Xs = np.random.default_rng(2).uniform(0, 1, size=(512, 4))
+    m, v = gp.predict(Xs, params, w, p)
+    assert bool(torch.isfinite(m).all()) and bool((v > 0).all()) and bool((v <= 1.0 + 1e-12).all())
+    P = PU.probit_predictive_distributions(params[1], m, v)
+    assert (P.sum(1) - 1).abs().max().item() < 1e-12 and bool((P >= 0).all())
+    del gp
+    torch.cuda.empty_cache()
+
+
 @pytest.mark.parametrize("policy", ["factor_every_step", "stale_factor_pcg", "nystrom_pcg", "nystrom_pcg_eq",
                                     "nystrom_pcg_sorted"])
 def test_newton_policies_agree(policy):

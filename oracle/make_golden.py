@@ -1,9 +1,10 @@
-"""Generates tests/golden/*.npz from the oracle (TEST INFRASTRUCTURE).
+"""Generates tests/golden/<case>.npz from the oracle (TEST INFRASTRUCTURE).
 
-The reference cannot be imported here (JAX / lab / mlkernels / jaxopt absent), so these
-fixtures are produced by the oracle in its LITERAL mode (dense Jacobian + LU Newton, LU predict) and
-committed; they freeze the oracle's outputs so that later edits to either the oracle or the CUDA path
-are caught.  Re-run:  python oracle/make_golden.py
+These fixtures hold the INPUTS of each case (X, y, test points, parameters) and the oracle's outputs in its
+LITERAL mode (dense Jacobian + LU Newton, LU predict); they freeze the oracle so that later edits to either the
+oracle or the CUDA path are caught.  The reference's own outputs on the same inputs are produced separately by
+oracle/make_reference_golden.py (reference source executed over the dependency shim) as tests/golden/ref_<case>.npz.
+Existing files are left untouched unless --all is given.  Re-run:  python oracle/make_golden.py [--all]
 """
 import os
 import sys

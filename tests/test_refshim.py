@@ -8,7 +8,6 @@ import subprocess
 import sys
 import textwrap
 
-import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

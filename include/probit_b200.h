@@ -51,6 +51,10 @@ typedef struct pb_kernel_spec {
     double stretch_in;  /* stretch applied before the periodic map (1 if none) */
     double period;      /* period p (ignored unless periodic) */
     double stretch_out; /* stretch applied to the features handed to the base kernel */
+    int32_t distance_form; /* 0: r^2 = sum_d (a_d - b_d)^2 (the product); 1: lab's B.pw_dists2 expansion
+                              ||a||^2 + ||b||^2 - 2 a.b with sqrt(max(., 1e-30)) (TEST-ONLY: reproduces the
+                              reference's O(1e-8) diagonal noise for Matern12, D > 1) */
+    int32_t _pad;
 } pb_kernel_spec;
 
 /* ---- likelihood specification ---------------------------------------------------------------
@@ -75,12 +79,26 @@ typedef struct pb_likelihood_spec {
 
 int pb_version(void);
 const char* pb_last_error(void);
-/* Tunables: "laplace_pcg_min_n" (smallest N at which Newton steps are solved by preconditioned CG instead of a
- * fresh factorisation; default 24576, 0 = always, huge = never), "laplace_nystrom_rank" (landmarks of the
- * Nystrom CG preconditioner: -1 = auto = n/16 clamped to [256, 4096], 0 = off, i.e. factor once and reuse the
- * stale factor as the preconditioner), "laplace_cg_tol" (eta: a CG Newton solve stops once the error it leaves in
- * the step is <= eta * tolerance, default 1e-2; floor 1e-15 relative residual), "potrf_block" (panel width, 0 = auto), "potrf_lookahead" (0/1). */
-int pb_set_option(const char* name, double value);
+
+/* Tunables of the drivers.  The library keeps NO mutable global configuration: every driver that has a policy to
+ * choose takes a `const pb_options*` (NULL = the defaults below), so concurrent callers on different host threads
+ * (XLA runs FFI handlers from several) cannot disturb one another.  Fill with pb_options_default() first. */
+typedef struct pb_options {
+    int64_t laplace_pcg_min_n;    /* smallest N at which Newton steps are solved by preconditioned CG instead of a
+                                     fresh factorisation; default 24576, 0 = always, huge = never */
+    int64_t laplace_nystrom_rank; /* landmarks of the Nystrom CG preconditioner: -1 = auto = n/16 clamped to
+                                     [256, 4096]; 0 = off (factor once, reuse the stale factor as preconditioner) */
+    double laplace_cg_tol;        /* eta: a CG Newton solve stops once the error it leaves in the step is
+                                     <= eta * tolerance; default 1e-2 (floor: 1e-15 relative residual) */
+    double negative_curvature_tol; /* W = -h may be slightly negative where Z << eps (utilities.py:57); values in
+                                     [-tol / sigma^2, 0) are treated as 0, anything below (or NaN) is PB_ERR_NUMERIC;
+                                     default 1e-6 */
+    int32_t potrf_block;          /* Cholesky panel width, 0 = auto */
+    int32_t potrf_lookahead;      /* 0/1, default 1 */
+    int32_t potrf_graph;          /* 1 (default): replay the factorisation's launch DAG from a cached CUDA graph */
+    int32_t dist_block;           /* panel width of the multi-GPU block-cyclic factorisation, 0 = auto */
+} pb_options;
+int pb_options_default(pb_options* options);
 
 /* Measurement hooks used by bench.py: total kernel launches issued by this library so far, and
  * CUDA-event timing (on the launching stream) of the trailing-update GEMM kernel between
@@ -88,6 +106,10 @@ int pb_set_option(const char* name, double value);
 long long pb_launch_count(void);
 int pb_profile_begin(void);
 int pb_profile_end(long long* gemm_launches, double* gemm_ms, double* gemm_flops);
+/* FP64 tensor-core (DMMA) peak of the current device in TFLOP/s, from a register-resident mma.sync loop run on the
+ * default stream (synchronises it): the denominator of the Cholesky roofline fractions (MEASURED_PEAKS.json has no
+ * FP64 entry).  ~50 ms. */
+int pb_measure_fp64_tensor_peak(double* tflops_host);
 
 /* ---- K4: fused per-datum likelihood (value, gradient, Hessian, third derivative) --------------
  * probit/approximators.py:96-104.  y is int64 class labels (ordinal) or f64 targets (Gaussian).
@@ -126,7 +148,7 @@ int pb_copy_lower_add_diag(pb_stream_t stream, const double* K, int64_t n, int64
  * `info` (device int32): 0, or 1-based column of the first non-positive pivot.                   */
 int64_t pb_potrf_workspace_bytes(int64_t n);
 int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,
-             int64_t workspace_bytes, int32_t* info);
+             int64_t workspace_bytes, int32_t* info, const pb_options* options);
 
 /* Fill the solve workspace (64x64 leaf inverses + 256x256 diagonal-block inverses used by pb_trsv /
  * pb_trsm_right_lt) for a factor L that was produced elsewhere (multi-GPU block-cyclic Cholesky). */
@@ -204,21 +226,6 @@ typedef struct pb_problem {
 /* Workspace layout is private; size it with pb_fit_workspace_bytes(n, D).  It holds K (n x ld),
  * the factor buffer (n x ld), features and O(n) vectors. */
 int64_t pb_fit_workspace_bytes(int64_t n, int D);
-/* External factorisation hook (SURVEY.md §8e "large-N Cholesky"): when set, every factorisation inside the
- * fit / predict drivers — a I + s s^T o (K + jitter I) -> lower factor in `L` plus the solve workspace —
- * is delegated to `fn` (the multi-GPU block-cyclic Cholesky of probit_b200/distributed.py, which broadcasts
- * panels with NCCL).  The callback must leave the factor in the lower triangle of L, fill
- * `potrf_workspace` (pb_rebuild_solve_workspace) and set *info_dev.  NULL restores the single-GPU path. */
-typedef int (*pb_factor_fn)(void* user, pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* s,
-                            double a, double jitter, double* L, int64_t ldl, void* potrf_workspace,
-                            int64_t potrf_workspace_bytes, int32_t* info_dev);
-int pb_set_factor_callback(pb_factor_fn fn, void* user);
-/* Optional replacement of y = K x inside the Newton / CG iterations of pb_laplace_fit (the one O(N^2) operation of
- * a CG step): multi-GPU jobs shard the rows of K over the ranks and all-gather y (probit_b200/distributed.py).
- * Every rank must return the same y.  NULL restores the single-GPU kernels. */
-typedef int (*pb_matvec_fn)(void* user, pb_stream_t stream, const double* K, int64_t n, int64_t ldk, const double* x,
-                            double* y);
-int pb_set_matvec_callback(pb_matvec_fn fn, void* user);
 /* Build features + K(theta) into the workspace (what every fit does first); and locate K inside it. */
 int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes);
 /* Features of the training inputs only (all that a mean-only pb_predict with variance == NULL needs). */
@@ -226,10 +233,11 @@ int pb_build_features(pb_stream_t stream, const pb_problem* prob, void* workspac
 int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, int64_t* ldk);
 int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
                    double jitter, int32_t final_factor, void* workspace, int64_t workspace_bytes,
-                   double* weight, double* precision, double* posterior_mean, pb_fit_result* result_host);
+                   double* weight, double* precision, double* posterior_mean, pb_fit_result* result_host,
+                   const pb_options* options);
 int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
               void* workspace, int64_t workspace_bytes, double* weight, double* precision,
-              double* posterior_mean, pb_fit_result* result_host);
+              double* posterior_mean, pb_fit_result* result_host, const pb_options* options);
 
 /* ---- A11: evidence gradient ("next" row 1) ------------------------------------------------------
  * d objective_LA / d (kernel scale, kernel stretch_out, noise std) at the converged weight: the closed form
@@ -243,13 +251,14 @@ int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int3
 int64_t pb_gradient_scratch_bytes(int64_t n);
 int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                         const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
-                        double* grad_host, int32_t grad_len);
+                        double* grad_host, int32_t grad_len, const pb_options* options);
 /* The same for objective_VB at the fixed point of f_VB (VBGP.value_and_grad, approximators.py:132-134,316-330;
  * VB.py:4-40): closed form of the implicit-function gradient (oracle/gradients.py::vb_gradient).  Factors
  * sigma^2 I + K and sigma I + W^1/2 K W^1/2 in the workspace (any factor held there is overwritten).
  * grad_host layout as above; scratch as pb_gradient_scratch_bytes(n). */
 int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
-                   const double* weight, void* scratch, int64_t scratch_bytes, double* grad_host, int32_t grad_len);
+                   const double* weight, void* scratch, int64_t scratch_bytes, double* grad_host, int32_t grad_len,
+                   const pb_options* options);
 
 /* ---- A10: predict -----------------------------------------------------------------------------
  * Approximator.predict (approximators.py:154-180): mean = K_*f w,
@@ -260,7 +269,8 @@ int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, 
  * of pb_predict_scratch_bytes(n, chunk) (cross-covariance tiles are generated on the fly and
  * never exist for more than one chunk).                                                         */
 int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, const double* precision,
-                       int32_t reuse_gram, void* workspace, int64_t workspace_bytes, int32_t* info_host);
+                       int32_t reuse_gram, void* workspace, int64_t workspace_bytes, int32_t* info_host,
+                       const pb_options* options);
 int64_t pb_predict_scratch_bytes(int64_t n, int D, int64_t chunk);
 int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace, const double* weight,
                const double* X_test, int64_t n_test, int64_t chunk, void* scratch, int64_t scratch_bytes,
@@ -272,6 +282,46 @@ int pb_predict(pb_stream_t stream, const pb_problem* prob, const void* workspace
 int pb_predict_covariance(pb_stream_t stream, const pb_problem* prob, const void* workspace,
                           const double* X_test, int64_t n_test, void* scratch, int64_t scratch_bytes,
                           double* cov, int64_t ldc);
+
+/* ---- ONE fit + predict partitioned over the GPUs of a box -----------------------------------
+ * One process per GPU.  The reference has no distributed code; these entry points partition
+ * exactly the path above: `LaplaceGP.approximate_posterior` (approximators.py:204-210 over solvers.py:18-25,
+ * Laplace.py:4-9) and `Approximator.predict` (approximators.py:154-180) for ONE training set of n points.
+ *
+ * pb_comm wraps an NCCL communicator (libnccl.so.2 is reached through dlopen, the single-GPU entry points do not
+ * need it) plus the library's communication / look-ahead streams.  Rank 0 calls pb_comm_unique_id, the 128 bytes
+ * travel to the other ranks by any means (torch.distributed, MPI, a file), every rank calls pb_comm_create on its
+ * own device.  world == 1 needs neither NCCL nor an id.  Every collective is enqueued on a CUDA stream from inside
+ * the library; every rank must make the same sequence of pb_dist_* calls.
+ *
+ * pb_dist_laplace_fit: the Newton loop of pb_laplace_fit with the rows of K sharded (each rank generates and keeps
+ *   K[lo:hi, :] only), y = K x as a local row-block product + one in-place all-gather of 8n bytes, and the Nystrom
+ *   preconditioner split by columns (one r x r all-reduce per Newton step).  Outputs (weight, precision, posterior
+ *   mean: n doubles each) are complete and identical on every rank.
+ * pb_dist_predict: factors B = I + P^1/2 (K + jitter I) P^1/2 in a 1-D block-column-cyclic layout (every rank fills
+ *   and keeps only its own block columns; panels travel by ncclBroadcast, overlapped with the trailing DMMA
+ *   updates) and, in the same sweep over the panels, solves for this rank's `n_test` LOCAL test points (test points
+ *   are sharded by the caller; there is no collective on the data path).  `chunk` rows of s o k(X*, X) are in flight at
+ *   a time (scratch: pb_dist_predict_scratch_bytes(n, D, min(chunk, n_test))); further chunks re-stream the stored
+ *   panels.  reuse_factor != 0: the workspace still holds the factor of a previous call with the same (theta,
+ *   precision) — skip the factorisation.  n_test may be 0 (factor + log-determinant only: the objective).
+ *   logdet_host (may be NULL) receives sum log diag chol(B), the last two terms of objective_LA (Laplace.py:24-30).
+ *   variance == NULL: means only (no factorisation unless logdet_host is given).                                  */
+typedef struct pb_comm pb_comm;
+int pb_comm_unique_id(void* id_host_128_bytes);
+int pb_comm_create(const void* id_host_128_bytes, int32_t rank, int32_t world, pb_comm** comm);
+int pb_comm_destroy(pb_comm* comm);
+int pb_comm_rank(const pb_comm* comm);
+int pb_comm_size(const pb_comm* comm);
+int64_t pb_dist_workspace_bytes(int64_t n, int D, int32_t world, int32_t rank, const pb_options* options);
+int pb_dist_laplace_fit(pb_stream_t stream, pb_comm* comm, const pb_problem* prob, double tolerance, int32_t maxiter,
+                        void* workspace, int64_t workspace_bytes, double* weight, double* precision,
+                        double* posterior_mean, pb_fit_result* result_host, const pb_options* options);
+int64_t pb_dist_predict_scratch_bytes(int64_t n, int D, int64_t rows);
+int pb_dist_predict(pb_stream_t stream, pb_comm* comm, const pb_problem* prob, const double* precision,
+                    const double* weight, void* workspace, int64_t workspace_bytes, double jitter, int32_t reuse_factor,
+                    const double* X_test, int64_t n_test, int64_t chunk, void* scratch, int64_t scratch_bytes,
+                    double* mean, double* variance, double* logdet_host, int32_t* info_host, const pb_options* options);
 
 /* ---- K15: ordinal predictive distributions (probit/utilities.py:232-249) ----------------------
  * out[n_test x J] = Phi((b[j+1]-m)/s) - Phi((b[j]-m)/s), s = sqrt(var + sigma^2).                */

@@ -17,7 +17,15 @@ PB_LIK_ORDINAL_PROBIT, PB_LIK_GAUSSIAN, PB_LIK_ORDINAL_PROBIT_SAFE = 0, 1, 2
 
 class KernelSpec(C.Structure):
     _fields_ = [("base", C.c_int32), ("periodic", C.c_int32), ("scale", C.c_double),
-                ("stretch_in", C.c_double), ("period", C.c_double), ("stretch_out", C.c_double)]
+                ("stretch_in", C.c_double), ("period", C.c_double), ("stretch_out", C.c_double),
+                ("distance_form", C.c_int32), ("_pad", C.c_int32)]
+
+
+class Options(C.Structure):
+    """pb_options: the tunables of the drivers, passed explicitly with every call (no global configuration)."""
+    _fields_ = [("laplace_pcg_min_n", C.c_int64), ("laplace_nystrom_rank", C.c_int64), ("laplace_cg_tol", C.c_double),
+                ("negative_curvature_tol", C.c_double), ("potrf_block", C.c_int32), ("potrf_lookahead", C.c_int32),
+                ("potrf_graph", C.c_int32), ("dist_block", C.c_int32)]
 
 
 class LikelihoodSpec(C.Structure):
@@ -47,19 +55,17 @@ class NumericError(ProbitB200Error):
 
 
 _p, _i32, _i64, _f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_double
-MATVEC_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p)
-FACTOR_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_double,
-                        C.c_double, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p)
-_SPEC, _LIK, _PROB = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER(Problem)
+_SPEC, _LIK, _PROB, _OPT = C.POINTER(KernelSpec), C.POINTER(LikelihoodSpec), C.POINTER(Problem), C.POINTER(Options)
 
 # name -> (restype, argtypes); mirrors include/probit_b200.h one to one
 SIGNATURES = {
     "pb_version": (_i32, []),
     "pb_last_error": (C.c_char_p, []),
-    "pb_set_option": (_i32, [C.c_char_p, _f64]),
+    "pb_options_default": (_i32, [_OPT]),
     "pb_launch_count": (C.c_longlong, []),
     "pb_profile_begin": (_i32, []),
     "pb_profile_end": (_i32, [C.POINTER(C.c_longlong), C.POINTER(_f64), C.POINTER(_f64)]),
+    "pb_measure_fp64_tensor_peak": (_i32, [C.POINTER(_f64)]),
     "pb_likelihood": (_i32, [_p, _LIK, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "pb_predictive_distributions": (_i32, [_p, _LIK, _p, _p, _i64, _p]),
     "pb_feature_dim": (_i32, [_SPEC, _i32]),
@@ -69,15 +75,13 @@ SIGNATURES = {
     "pb_scale_sym_plus_identity": (_i32, [_p, _p, _i64, _i64, _p, _f64, _p, _i64]),
     "pb_copy_lower_add_diag": (_i32, [_p, _p, _i64, _i64, _f64, _p, _i64]),
     "pb_potrf_workspace_bytes": (_i64, [_i64]),
-    "pb_potrf": (_i32, [_p, _p, _i64, _i64, _p, _i64, _p]),
+    "pb_potrf": (_i32, [_p, _p, _i64, _i64, _p, _i64, _p, _OPT]),
     "pb_rebuild_solve_workspace": (_i32, [_p, _p, _i64, _i64, _p, _i64]),
     "pb_transform_block": (_i32, [_p, _p, _i64, _p, _f64, _f64, _i64, _i64, _i64, _i64, _p, _i64]),
-    "pb_set_factor_callback": (_i32, [_p, _p]),
     "pb_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _f64, _p, _i64, _i32]),
     "pb_symv": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "pb_symv_lower_scratch_bytes": (_i64, [_i64]),
     "pb_gemv": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p]),
-    "pb_set_matvec_callback": (_i32, [_p, _p]),
     "pb_symv_lower": (_i32, [_p, _p, _i64, _i64, _p, _p, _p, _i64]),
     "pb_trsv": (_i32, [_p, _p, _i64, _i64, _p, _i32, _p, _p]),
     "pb_logdet_chol": (_i32, [_p, _p, _i64, _i64, _p]),
@@ -86,15 +90,25 @@ SIGNATURES = {
     "pb_build_gram": (_i32, [_p, _PROB, _p, _i64]),
     "pb_build_features": (_i32, [_p, _PROB, _p, _i64]),
     "pb_workspace_gram": (_i32, [_p, _i64, _i32, C.POINTER(_p), C.POINTER(_i64)]),
-    "pb_laplace_fit": (_i32, [_p, _PROB, _f64, _i32, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult)]),
-    "pb_vb_fit": (_i32, [_p, _PROB, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult)]),
+    "pb_laplace_fit": (_i32, [_p, _PROB, _f64, _i32, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult), _OPT]),
+    "pb_vb_fit": (_i32, [_p, _PROB, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult), _OPT]),
     "pb_gradient_scratch_bytes": (_i64, [_i64]),
-    "pb_laplace_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _p, _i64, C.POINTER(_f64), _i32]),
-    "pb_vb_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _i64, C.POINTER(_f64), _i32]),
-    "pb_predict_prepare": (_i32, [_p, _PROB, _p, _i32, _p, _i64, C.POINTER(_i32)]),
+    "pb_laplace_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _p, _i64, C.POINTER(_f64), _i32, _OPT]),
+    "pb_vb_gradient": (_i32, [_p, _PROB, _p, _i64, _p, _p, _i64, C.POINTER(_f64), _i32, _OPT]),
+    "pb_predict_prepare": (_i32, [_p, _PROB, _p, _i32, _p, _i64, C.POINTER(_i32), _OPT]),
     "pb_predict_scratch_bytes": (_i64, [_i64, _i32, _i64]),
     "pb_predict_covariance": (_i32, [_p, _PROB, _p, _p, _i64, _p, _i64, _p, _i64]),
     "pb_predict": (_i32, [_p, _PROB, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p]),
+    "pb_comm_unique_id": (_i32, [_p]),
+    "pb_comm_create": (_i32, [_p, _i32, _i32, C.POINTER(_p)]),
+    "pb_comm_destroy": (_i32, [_p]),
+    "pb_comm_rank": (_i32, [_p]),
+    "pb_comm_size": (_i32, [_p]),
+    "pb_dist_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32, _OPT]),
+    "pb_dist_laplace_fit": (_i32, [_p, _p, _PROB, _f64, _i32, _p, _i64, _p, _p, _p, C.POINTER(FitResult), _OPT]),
+    "pb_dist_predict_scratch_bytes": (_i64, [_i64, _i32, _i64]),
+    "pb_dist_predict": (_i32, [_p, _p, _PROB, _p, _p, _p, _i64, _f64, _i32, _p, _i64, _i64, _p, _i64, _p, _p,
+                               C.POINTER(_f64), C.POINTER(_i32), _OPT]),
 }
 
 _lib = None
@@ -117,8 +131,15 @@ def load():
     return lib
 
 
-def set_option(name, value):
-    check(load().pb_set_option(name.encode(), float(value)))
+def default_options(**overrides):
+    """A pb_options filled with the library defaults, then `overrides` (field name -> value)."""
+    o = Options()
+    check(load().pb_options_default(C.byref(o)))
+    for name, value in overrides.items():
+        if name not in dict((f[0], 1) for f in Options._fields_):
+            raise KeyError(f"unknown option {name!r}")
+        setattr(o, name, type(getattr(o, name))(value))
+    return o
 
 
 def check(status):

@@ -53,7 +53,7 @@ class Approximator(ABC):
 
     def __init__(self, data, prior, log_likelihood, grad_log_likelihood=None, hessian_log_likelihood=None,
                  tolerance=1e-5, maxiter=100, jitter=1e-12, likelihood_eps=_util.LIKELIHOOD_EPS,
-                 predict_chunk=None):
+                 predict_chunk=None, options=None, distance_form="direct"):
         self.tolerance = tolerance                      # approximators.py:90
         self.maxiter = maxiter                          # jaxopt FixedPointIteration default
         self.jitter = jitter                            # lab's B.epsilon in B.cholesky(Dense) (Laplace.py:24)
@@ -62,6 +62,11 @@ class Approximator(ABC):
         self.log_likelihood = log_likelihood
         self._kind = _likelihood_kind(log_likelihood, grad_log_likelihood, hessian_log_likelihood)
         self.lib = _lib.load()
+        # driver tunables (pb_options), passed with every call: `options` is a dict of field overrides
+        self.options = _lib.default_options(**(options or {}))
+        if distance_form not in ("direct", "expand"):
+            raise ValueError("distance_form must be 'direct' (the product) or 'expand' (test-only: lab's pw_dists2 form)")
+        self._distance_form = 1 if distance_form == "expand" else 0
         X_train, y_train = data
         # float32 inputs (the reference without jax_enable_x64, BASELINE configs[0]) are promoted to float64 on the
         # device — the FP64 path is the product — and results are handed back in the input precision.
@@ -88,7 +93,7 @@ class Approximator(ABC):
 
     def _spec(self, prior_parameters):
         kernel = _kernels.as_kernel(self.prior(prior_parameters))
-        return kernel.lower()
+        return kernel.lower(self._distance_form)
 
     def _problem(self, parameters):
         prior_parameters, likelihood_parameters = parameters
@@ -180,7 +185,7 @@ class Approximator(ABC):
             reuse_gram = int(self._gram_key == key)
             self._gram_key, self._factor_key = None, None
             _lib.check(self.lib.pb_predict_prepare(_stream(), C.byref(prob), _ptr(precision), reuse_gram, _ptr(ws),
-                                                   self._ws_bytes, C.byref(info)))
+                                                   self._ws_bytes, C.byref(info), C.byref(self.options)))
             self._gram_key, self._factor_key = key, (key, precision.clone())
         return ws
 
@@ -246,7 +251,7 @@ class LaplaceGP(Approximator):
         self._gram_key, self._factor_key = None, None
         status = self.lib.pb_laplace_fit(_stream(), C.byref(prob), float(self.tolerance), int(self.maxiter),
                                          float(self.jitter), int(final_factor), _ptr(ws), self._ws_bytes, _ptr(w),
-                                         _ptr(p), _ptr(f), C.byref(res))
+                                         _ptr(p), _ptr(f), C.byref(res), C.byref(self.options))
         self.last_result = res
         _lib.check(status)
         self._gram_key = self._spec_key(prob.kernel)
@@ -330,10 +335,10 @@ def _closed_form_value_and_grad(self):
         self._factor_key = None
         if laplace:
             _lib.check(self.lib.pb_laplace_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w), _ptr(p),
-                                                    _ptr(scratch), sbytes, g3, glen))
+                                                    _ptr(scratch), sbytes, g3, glen, C.byref(self.options)))
         else:
             _lib.check(self.lib.pb_vb_gradient(_stream(), C.byref(prob), _ptr(ws), self._ws_bytes, _ptr(w),
-                                               _ptr(scratch), sbytes, g3, glen))
+                                               _ptr(scratch), sbytes, g3, glen, C.byref(self.options)))
         del keep, scratch
         d_scale, d_stretch, d_sigma = g3[0], g3[1], g3[2]
         flat, rebuild = _flatten_scalars(prior_parameters)
@@ -375,7 +380,7 @@ class VBGP(Approximator):
         res = _lib.FitResult()
         self._gram_key, self._factor_key = None, None
         status = self.lib.pb_vb_fit(_stream(), C.byref(prob), float(self.tolerance), int(self.maxiter), _ptr(ws),
-                                    self._ws_bytes, _ptr(w), _ptr(p), _ptr(f), C.byref(res))
+                                    self._ws_bytes, _ptr(w), _ptr(p), _ptr(f), C.byref(res), C.byref(self.options))
         self.last_result = res
         _lib.check(status)
         self._gram_key = self._spec_key(prob.kernel)

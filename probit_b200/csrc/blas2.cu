@@ -528,10 +528,9 @@ int trsv(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const dou
 // Builds the TB-block inverses behind the leaf inverses in the potrf workspace (called at the end of potrf).
 int build_block_inverses(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, double* dinv) {
     if (n == 0) return PB_OK;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         PB_CUDA(cudaFuncSetAttribute(tb_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TBINV_SMEM));
-        configured = true;
     }
     double* tinv = dinv + ceil_div<int64_t>(n, LEAF) * LEAF * LEAF;
     const int64_t nblk = ceil_div<int64_t>(n, TB);

@@ -29,29 +29,31 @@ void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops) {
     g_gemm.push_back({e0, e1, flops});
 }
 
-// Tunables (pb_set_option); defaults chosen from measurements on B200.
-static std::atomic<long long> g_pcg_min_n{24576};     // PCG Newton steps pay off once potrf >> trsv
-static std::atomic<long long> g_nystrom_rank{-1};     // -1 = automatic (n/16 clamped to [256, 4096]), 0 = off
-static std::atomic<double> g_cg_tol{1e-2};            // CG Newton solves: error of the step <= this * Newton tolerance
-static std::atomic<int> g_potrf_nb{0};                // 0 = automatic
-static std::atomic<int> g_lookahead{1};
+// Tunables: immutable defaults + a per-thread pointer to the options of the driver call in flight.
+static pb_options default_options() {
+    pb_options o;
+    o.laplace_pcg_min_n = 24576;       // PCG Newton steps pay off once potrf >> trsv
+    o.laplace_nystrom_rank = -1;       // automatic (n/16 clamped to [256, 4096])
+    o.laplace_cg_tol = 1e-2;           // CG Newton solves: error of the step <= this * Newton tolerance
+    o.negative_curvature_tol = 1e-6;
+    o.potrf_block = 0;
+    o.potrf_lookahead = 1;
+    o.potrf_graph = 1;
+    o.dist_block = 0;
+    return o;
+}
+static const pb_options g_defaults = default_options();
+static thread_local const pb_options* tl_options = nullptr;
 
-long long opt_pcg_min_n() { return g_pcg_min_n.load(std::memory_order_relaxed); }
-long long opt_nystrom_rank() { return g_nystrom_rank.load(std::memory_order_relaxed); }
-double opt_cg_tol() { return g_cg_tol.load(std::memory_order_relaxed); }
-int opt_potrf_nb() { return g_potrf_nb.load(std::memory_order_relaxed); }
-bool opt_lookahead() { return g_lookahead.load(std::memory_order_relaxed) != 0; }
+const pb_options& opts() { return tl_options ? *tl_options : g_defaults; }
+OptScope::OptScope(const pb_options* o) : prev(tl_options) { if (o) tl_options = o; }
+OptScope::~OptScope() { tl_options = prev; }
 
 }  // namespace pb
 
-extern "C" int pb_set_option(const char* name, double value) {
-    PB_CHECK(name != nullptr, PB_ERR_INVALID, "set_option: null name");
-    if (!strcmp(name, "laplace_pcg_min_n")) pb::g_pcg_min_n.store((long long)value);
-    else if (!strcmp(name, "laplace_nystrom_rank")) pb::g_nystrom_rank.store((long long)value);
-    else if (!strcmp(name, "laplace_cg_tol")) pb::g_cg_tol.store(value);
-    else if (!strcmp(name, "potrf_block")) pb::g_potrf_nb.store((int)value);
-    else if (!strcmp(name, "potrf_lookahead")) pb::g_lookahead.store(value != 0.0);
-    else PB_CHECK(false, PB_ERR_INVALID, "set_option: unknown option '%s'", name);
+extern "C" int pb_options_default(pb_options* options) {
+    PB_CHECK(options != nullptr, PB_ERR_INVALID, "options_default: null argument");
+    *options = pb::g_defaults;
     return PB_OK;
 }
 
@@ -84,6 +86,57 @@ extern "C" int pb_profile_end(long long* gemm_launches, double* gemm_ms, double*
     return PB_OK;
 }
 
-extern "C" int pb_version(void) { return 100; }
+// Register-resident mma.sync.m16n8k8.f64 loop (SASS: DMMA.8x8x4): the FP64 tensor-core peak of THIS device, the
+// denominator of every "fraction of FP64 tensor peak" bench.py prints (MEASURED_PEAKS.json carries no FP64 entry).
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double c[8][4];
+    double a[4], b[2];
+    for (int i = 0; i < 4; ++i) a[i] = 1e-3 * (threadIdx.x + i);
+    for (int i = 0; i < 2; ++i) b[i] = 1e-3 * (threadIdx.x + 7 + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 4; ++i) c[j][i] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            asm volatile(
+                "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                : "+d"(c[j][0]), "+d"(c[j][1]), "+d"(c[j][2]), "+d"(c[j][3])
+                : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        for (int i = 0; i < 4; ++i) s += c[j][i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int pb_measure_fp64_tensor_peak(double* tflops_host) {
+    PB_CHECK(tflops_host != nullptr, PB_ERR_INVALID, "measure_fp64_tensor_peak: null argument");
+    const int grid = pb::num_sms() * 4, iters = 20000;
+    double* out = nullptr;
+    PB_CUDA(cudaMalloc(&out, sizeof(double) * grid * 256));
+    cudaEvent_t e0, e1;
+    PB_CUDA(cudaEventCreate(&e0));
+    PB_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {                 // first two are warm-up
+        PB_CUDA(cudaEventRecord(e0, 0));
+        dmma_peak_kernel<<<grid, 256>>>(out, iters);
+        PB_CUDA(cudaEventRecord(e1, 0));
+        PB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (r >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops_host = 2.0 * 16 * 8 * 8 * 8.0 * iters * (double)grid * 8 / best * 1e-9;
+    return PB_OK;
+}
+
+extern "C" int pb_version(void) { return 200; }
 
 extern "C" const char* pb_last_error(void) { return pb::g_error; }

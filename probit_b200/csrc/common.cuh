@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdarg>
 #include <cmath>
+#include <atomic>
 #include "../../include/probit_b200.h"
 
 namespace pb {
@@ -19,12 +20,30 @@ void note_launch();
 bool profiling_enabled();
 void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops);
 
-// tunables set through pb_set_option (capi.cu)
-long long opt_pcg_min_n();
-long long opt_nystrom_rank();
-double opt_cg_tol();
-int opt_potrf_nb();
-bool opt_lookahead();
+// Tunables (capi.cu).  There is no mutable global configuration: an extern "C" driver installs the caller's
+// pb_options for the duration of its call on the calling thread (OptScope); everything below it reads them here.
+const pb_options& opts();
+struct OptScope {
+    const pb_options* prev;
+    explicit OptScope(const pb_options* o);
+    ~OptScope();
+};
+inline long long opt_pcg_min_n() { return opts().laplace_pcg_min_n; }
+inline long long opt_nystrom_rank() { return opts().laplace_nystrom_rank; }
+inline double opt_cg_tol() { return opts().laplace_cg_tol; }
+inline int opt_potrf_nb() { return opts().potrf_block; }
+inline bool opt_lookahead() { return opts().potrf_lookahead != 0; }
+
+// true exactly once per (call site, device): guards cudaFuncSetAttribute, which is a per-device setting
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    bool first() {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        const unsigned long long bit = 1ull << (dev & 63);
+        return (done.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+    }
+};
 
 #define PB_CUDA(expr)                                                                         \
     do {                                                                                      \
@@ -50,12 +69,14 @@ bool opt_lookahead();
     } while (0)
 
 inline int num_sms() {
-    static int n = 0;
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cache[dev & 63].store(n, std::memory_order_relaxed);
     }
     return n;
 }
@@ -139,6 +160,9 @@ int gram_sym(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, i
              double* K, int64_t ldk, const double* diag_vec, double diag_scalar);
 int gram_cross(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
                int64_t n2, int Df, int64_t ldz1, int64_t ldz2, double* K, int64_t ldk, const double* col_scale);
+int gram_block(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z, int64_t ldz, int Df, int64_t row0,
+               int64_t rows, int64_t col0, int64_t cols, const double* s, double a, double jitter, double* out,
+               int64_t ldo);
 int gram_matvec_splits(int64_t n1);
 int gram_matvec(cudaStream_t stream, const pb_kernel_spec& spec, const double* Z1, int64_t n1, const double* Z2,
                 int64_t n2, int Df, int64_t ldz1, int64_t ldz2, const double* v, double* partial, double* y);

@@ -13,67 +13,13 @@
 // (N^3/3 flops) and never divides by W.  The iterates agree with the LU form to ~1e-14
 // (tests/test_oracle_fit.py) and the iteration count is identical.
 #include "likelihood.cuh"
+#include "workspace.cuh"
 #include <cstdlib>
-#include <mutex>
 #include <vector>
 
 namespace pb {
 
 namespace {
-
-constexpr int VEC_BLOCKS_MAX = 1024;
-
-inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
-
-struct Layout {
-    int64_t n, ld;
-    int Dfmax;
-    // byte offsets
-    int64_t K, B, Z, potrf_ws, vec, partial, scalars, info, total;
-    int64_t vec_stride;   // doubles per vector slot
-};
-
-enum VecSlot { V_W = 0, V_WN, V_F, V_S, V_B, V_T, V_C, V_X, V_G, V_SF, V_E, V_R, V_Z, V_P, V_Q, V_Y, V_U, V_COUNT };
-enum Scalar { S_ERR2 = 0, S_SUMLL, S_FTW, S_LOGDET, S_BAD, S_PBP, S_RZ0, S_RZ1, S_RR, S_R0, S_G0, S_G1, S_G2, S_GD0, S_GD1, S_GSIG, S_COUNT = 16 };
-
-Layout make_layout(int64_t n, int D) {
-    Layout L;
-    L.n = n;
-    L.ld = round_up(n > 0 ? n : 1, 16);
-    L.Dfmax = 2 * D;
-    int64_t off = 0;
-    auto take = [&](int64_t bytes) { int64_t o = off; off += round_up(bytes, 256); return o; };
-    L.K = take(n * L.ld * 8);
-    L.B = take(n * L.ld * 8);
-    L.Z = take(n * (int64_t)L.Dfmax * 8);
-    L.potrf_ws = take(pb_potrf_workspace_bytes(n));
-    L.vec_stride = round_up(n > 0 ? n : 1, 32);
-    L.vec = take(L.vec_stride * V_COUNT * 8);
-    L.partial = take(VEC_BLOCKS_MAX * 2 * 8);
-    L.scalars = take(S_COUNT * 8);
-    L.info = take(256);
-    L.total = off;
-    return L;
-}
-
-struct Ws {
-    Layout L;
-    uint8_t* base;
-    double* K() const { return reinterpret_cast<double*>(base + L.K); }
-    double* B() const { return reinterpret_cast<double*>(base + L.B); }
-    double* Z() const { return reinterpret_cast<double*>(base + L.Z); }
-    void* potrf_ws() const { return base + L.potrf_ws; }
-    double* dinv() const { return reinterpret_cast<double*>(base + L.potrf_ws); }
-    double* vec(int slot) const { return reinterpret_cast<double*>(base + L.vec) + slot * L.vec_stride; }
-    double* partial() const { return reinterpret_cast<double*>(base + L.partial); }
-    double* scalars() const { return reinterpret_cast<double*>(base + L.scalars); }
-    int32_t* info() const { return reinterpret_cast<int32_t*>(base + L.info); }
-};
-
-inline unsigned vec_blocks(int64_t n) {
-    int64_t b = ceil_div<int64_t>(n, 256);
-    return (unsigned)(b < 1 ? 1 : (b > VEC_BLOCKS_MAX ? VEC_BLOCKS_MAX : b));
-}
 
 // two partial sums per block -> partial[2*block + k]
 __device__ __forceinline__ void write_partials(double a, double b, double* partial) {
@@ -104,16 +50,21 @@ finalize_kernel(const double* __restrict__ partial, int nblk, double* out0, doub
 // partials: sum ll, number of data with W < 0 or NaN.
 __global__ void __launch_bounds__(256)
 laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
-                    const void* __restrict__ y, int64_t n, double* __restrict__ s, double* __restrict__ b,
-                    double* __restrict__ partial) {
+                    const void* __restrict__ y, int64_t n, double neg_floor, double* __restrict__ s,
+                    double* __restrict__ b, double* __restrict__ partial) {
     __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double fi = f[i];
         const lik::Out o = lik::eval(p, fi, y, i, sc);
-        const double W = -o.h;
-        if (!(W >= 0.0)) bad += 1.0;
+        double W = -o.h;
+        // log(Z + 1e-10) is not log-concave where Z << 1e-10 (far tails): h there is ~ +1e-9, which the
+        // reference's LU Newton step simply carries along.  The SPD form treats that datum as W = 0 for this
+        // step (same fixed point: the step solves a slightly different linearisation); only a materially
+        // negative or NaN curvature is an error.
+        if (!(W >= neg_floor)) bad += 1.0;
+        W = W > 0.0 ? W : 0.0;
         s[i] = sqrt(W);
         b[i] = fma(W, fi, o.g);
         sum_ll += o.ll;
@@ -158,12 +109,13 @@ mul_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n
 }
 
 __global__ void __launch_bounds__(256)
-sqrt_kernel(const double* __restrict__ a, int64_t n, double* __restrict__ out, double* __restrict__ partial) {
+sqrt_kernel(const double* __restrict__ a, int64_t n, double neg_floor, double* __restrict__ out,
+            double* __restrict__ partial) {
     double bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double v = a[i];
-        if (!(v >= 0.0)) bad += 1.0;
-        out[i] = sqrt(v);
+        if (!(v >= neg_floor)) bad += 1.0;
+        out[i] = sqrt(v > 0.0 ? v : 0.0);      // a precision in [neg_floor, 0) is a datum that carries no information
     }
     write_partials(0.0, bad, partial);
 }
@@ -316,12 +268,16 @@ pcg_dir_kernel(const double* __restrict__ sc_new, const double* __restrict__ sc_
 __global__ void __launch_bounds__(256)
 grad_s2_kernel(const double* __restrict__ neg_binv_diag, const double* __restrict__ W, const double* __restrict__ d3,
                const double* __restrict__ f, const void* __restrict__ y, int gaussian, double sigma, int64_t n,
-               double* __restrict__ s2, double* __restrict__ Vout, double* __restrict__ partial) {
+               double neg_floor, double kss, double* __restrict__ s2, double* __restrict__ Vout,
+               double* __restrict__ partial) {
     double acc = 0, bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double w = W[i];
-        if (!(w > 0.0)) bad += 1.0;
-        const double V = (1.0 + neg_binv_diag[i]) / w;       // neg_binv_diag = -sum_k U_ik^2 = -(B^-1)_ii
+        if (!(w >= neg_floor)) bad += 1.0;
+        // neg_binv_diag = -sum_k U_ik^2 = -(B^-1)_ii.  A datum whose curvature was clamped to 0 (Z << eps: every
+        // derivative of log(Z + eps) is ~1e-9 there, so V only ever multiplies ~0) gets the prior variance, the
+        // bound V_i <= K_ii.
+        const double V = w > 0.0 ? (1.0 + neg_binv_diag[i]) / w : kss;
         Vout[i] = V;
         s2[i] = 0.5 * V * d3[i];
         if (gaussian) {
@@ -423,6 +379,9 @@ int bind(const pb_problem* prob, void* workspace, int64_t workspace_bytes, Ws& w
 int build_gram(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
     const int Df = feature_dim(prob->kernel, prob->D);
     PB_TRY(features(st, prob->kernel, prob->X, prob->n, prob->D, prob->D, ws.Z(), prob->n));
+    if (ws.dist)      // this rank's rows of K only, straight from the features: K[lo:hi, :] = k(Z[lo:hi], Z)
+        return gram_cross(st, prob->kernel, ws.Z() + ws.dist->lo, ws.dist->hi - ws.dist->lo, ws.Z(), prob->n, Df, prob->n,
+                          prob->n, ws.K(), ws.L.ld, nullptr);
     return gram_sym(st, prob->kernel, ws.Z(), prob->n, Df, prob->n, ws.K(), ws.L.ld, nullptr, 0.0);
 }
 
@@ -439,11 +398,13 @@ int read_scalars(cudaStream_t st, const Ws& ws, double* host, int32_t* info_host
     return PB_OK;
 }
 
+int K_times(cudaStream_t st, const Ws& ws, int64_t n, const double* x, double* y, double* symv_scratch);
+
 // posterior mean f = K w, precision, sum ll, f.w  -> device scalars
 int posterior_stats(cudaStream_t st, const pb_problem* prob, const lik::Params& lp, const Ws& ws, const double* w,
                     double* prec_out) {
     const int64_t n = prob->n;
-    PB_TRY(gemv(st, ws.K(), n, n, ws.L.ld, w, ws.vec(V_F)));
+    PB_TRY(K_times(st, ws, n, w, ws.vec(V_F), nullptr));
     const unsigned nb = vec_blocks(n);
     posterior_stats_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, w, n, prec_out,
                                                ws.partial()); pb::note_launch();
@@ -451,29 +412,14 @@ int posterior_stats(cudaStream_t st, const pb_problem* prob, const lik::Params& 
     return finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_FTW);
 }
 
-// Optional external factorisation (multi-GPU block-cyclic Cholesky, probit_b200/distributed.py).
-std::mutex g_factor_mu;
-pb_factor_fn g_factor_fn = nullptr;
-void* g_factor_user = nullptr;
-
-// Optional external y = K x (rows of K sharded over the ranks of a multi-GPU job, probit_b200/distributed.py).
-pb_matvec_fn g_matvec_fn = nullptr;
-void* g_matvec_user = nullptr;
-
-// y = K x for the Newton / CG iterations: the external product if one is installed, else the half-traffic symv
-// when its scratch is available, else the row-wise gemv.
+// y = K x for the Newton / CG iterations: the half-traffic symv when its scratch is available, else the row-wise gemv.
 int K_times(cudaStream_t st, const Ws& ws, int64_t n, const double* x, double* y, double* symv_scratch) {
-    pb_matvec_fn fn;
-    void* user;
-    {
-        std::lock_guard<std::mutex> lock(g_factor_mu);
-        fn = g_matvec_fn;
-        user = g_matvec_user;
-    }
-    if (fn) {
-        const int status = fn(user, reinterpret_cast<pb_stream_t>(st), ws.K(), n, ws.L.ld, x, y);
-        PB_CHECK(status == PB_OK, status, "external matvec callback failed with %d", status);
-        return PB_OK;
+    if (ws.dist) {
+        // rows of K sharded over the ranks: each streams its n/G rows (the product is HBM bound, so 1/G of the time),
+        // then ONE in-place all-gather of 8 n bytes enqueued on the same stream puts the same y on every rank
+        const DistCtx& d = *ws.dist;
+        PB_TRY(gemv(st, ws.K(), d.hi - d.lo, n, ws.L.ld, x, y + d.lo));
+        return comm_allgather(d.comm, st, y, d.nloc_max);
     }
     if (symv_scratch) return symv_lower(st, ws.K(), n, ws.L.ld, x, y, symv_scratch);
     return gemv(st, ws.K(), n, n, ws.L.ld, x, y);
@@ -481,19 +427,6 @@ int K_times(cudaStream_t st, const Ws& ws, int64_t n, const double* x, double* y
 
 // Factor a I + s s^T o (K + jitter I) into ws.B() (lower) and fill the solve workspace.
 int factor_matrix(cudaStream_t st, const Ws& ws, int64_t n, const double* s, double a, double jitter) {
-    pb_factor_fn fn;
-    void* user;
-    {
-        std::lock_guard<std::mutex> lock(g_factor_mu);
-        fn = g_factor_fn;
-        user = g_factor_user;
-    }
-    if (fn) {
-        const int status = fn(user, reinterpret_cast<pb_stream_t>(st), ws.K(), n, ws.L.ld, s, a, jitter, ws.B(), ws.L.ld,
-                              ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info());
-        PB_CHECK(status == PB_OK, status, "external factorisation callback failed with %d", status);
-        return PB_OK;
-    }
     PB_TRY(sym_transform(st, ws.K(), n, ws.L.ld, s, a, jitter, ws.B(), ws.L.ld));
     return potrf(st, ws.B(), n, ws.L.ld, ws.potrf_ws(), pb_potrf_workspace_bytes(n), ws.info());
 }
@@ -594,7 +527,9 @@ int pcg_solve(cudaStream_t st, const Ws& ws, int64_t n, const double* s, const d
 // need few without any help.  ws.B() is idle until the final factorisation, so everything lives there.
 struct Nystrom {
     int64_t r = 0, lda = 0, pws_bytes = 0;
-    double* G = nullptr;      // r x ld : K_IN S
+    int64_t ldg = 0, ncols = 0, col0 = 0;   // G covers columns [col0, col0 + ncols) (all of them on one GPU, the rank's shard otherwise)
+    double* Zl = nullptr;     // features of the landmarks, feature-major (multi-GPU only)
+    double* G = nullptr;      // r x ldg : K_IN S
     double* A = nullptr;      // r x lda
     double* pws = nullptr;    // potrf workspace of A
     double* t = nullptr;      // r
@@ -611,23 +546,34 @@ int64_t nystrom_rank(int64_t n) {
     return r;
 }
 
-Nystrom nystrom_layout(const Ws& ws, int64_t n) {
-    Nystrom ny;
-    ny.r = nystrom_rank(n);
-    if (ny.r <= 0) return ny;
+// Layout inside the (idle) factor region.  Returns the doubles used; `base` may be null (size query).
+int64_t nystrom_carve(Nystrom& ny, double* base, int64_t n, int64_t ld, int64_t ldg, int Dfmax, bool sharded) {
+    int64_t used = 0;
+    auto take = [&](int64_t doubles) { double* o = base ? base + used : nullptr; used += round_up(doubles, 32); return o; };
     ny.lda = round_up(ny.r, 16);
     ny.pws_bytes = pb_potrf_workspace_bytes(ny.r);
-    double* p = ws.B();
-    auto take = [&](int64_t doubles) { double* o = p; p += round_up(doubles, 32); return o; };
-    ny.G = take(ny.r * ws.L.ld);
+    ny.ldg = ldg;
+    ny.G = take(ny.r * ldg);
     ny.A = take(ny.r * ny.lda);
     ny.pws = take(ny.pws_bytes / 8 + 1);
     ny.t = take(ny.r);
     ny.u = take(ny.r);
-    ny.gt = take(gemv_t_splits(ny.r) * ws.L.ld);
+    ny.gt = take(gemv_t_splits(ny.r) * ldg);
     ny.stride = n / ny.r;
-    if (ws.L.ld >= round_up(n, 64)) ny.symv = take(symv_lower_scratch_doubles(n));
-    if (p - ws.B() > n * ws.L.ld) ny.r = 0;      // does not fit (tiny n): disabled
+    if (sharded) ny.Zl = take((int64_t)Dfmax * ny.r);
+    else if (ld >= round_up(n, 64)) ny.symv = take(symv_lower_scratch_doubles(n));
+    return used;
+}
+
+Nystrom nystrom_layout(const Ws& ws, int64_t n) {
+    Nystrom ny;
+    ny.r = nystrom_rank(n);
+    if (ny.r <= 0) return ny;
+    const bool sharded = ws.dist != nullptr;
+    ny.ncols = sharded ? ws.dist->hi - ws.dist->lo : n;
+    ny.col0 = sharded ? ws.dist->lo : 0;
+    const int64_t used = nystrom_carve(ny, ws.B(), n, ws.L.ld, sharded ? ws.dist->nloc_max : ws.L.ld, ws.L.Dfmax, sharded);
+    if (used > ws.L.B_doubles) ny.r = 0;      // does not fit (tiny n): disabled
     return ny;
 }
 
@@ -659,15 +605,44 @@ nystrom_z_kernel(const double* __restrict__ r, const double* __restrict__ vpart,
     write_partials(d, 0.0, partial);
 }
 
+// Zl[d][i] = Z[d][i * stride]: the landmarks' features, feature-major with leading dimension r
+__global__ void __launch_bounds__(256)
+gather_landmarks_kernel(const double* __restrict__ Z, int64_t ldz, int Df, int64_t r, int64_t stride,
+                        double* __restrict__ Zl) {
+    for (int64_t e = blockIdx.x * 256ll + threadIdx.x; e < (int64_t)Df * r; e += (int64_t)gridDim.x * 256) {
+        const int64_t d = e / r, i = e % r;
+        Zl[e] = Z[d * ldz + i * stride];
+    }
+}
+
 // Builds A for the current s and factors it; *ok = false if A is not numerically SPD.
-int nystrom_build(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, const double* s, double delta, bool* ok) {
+// Multi-GPU: G is split by columns — rank q holds G[:, lo_q:hi_q] = k(landmarks, X[lo_q:hi_q]) S, generated from the
+// features, forms its r x r x (n/G) share of G G^T on the tensor cores, and ONE all-reduce of the r x r block
+// (134 MB at r = 4096) completes A = K_II + delta I + G G^T on every rank; the r x r Cholesky is replicated.
+int nystrom_build(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, const double* s, double delta, bool* ok,
+                  const pb_problem* prob) {
     const int64_t ld = ws.L.ld;
     int32_t* info = ws.info() + 1;
     PB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-    dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), 64), (unsigned)ny.r);
-    nystrom_prep_kernel<<<grid, 256, 0, st>>>(ws.K(), ld, s, n, ny.r, ny.stride, delta, ny.G, ny.A, ny.lda); pb::note_launch();
-    PB_CUDA(cudaGetLastError());
-    PB_TRY(gemm_nt(st, ny.r, ny.r, n, 1.0, ny.G, ld, ny.G, ld, 1.0, ny.A, ny.lda, true));
+    if (ws.dist) {
+        const DistCtx& d = *ws.dist;
+        const int Df = feature_dim(prob->kernel, prob->D);
+        gather_landmarks_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(Df * ny.r, 256), 1024), 256, 0, st>>>(
+            ws.Z(), n, Df, ny.r, ny.stride, ny.Zl); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        if (d.comm->rank == 0) PB_TRY(gram_sym(st, prob->kernel, ny.Zl, ny.r, Df, ny.r, ny.A, ny.lda, nullptr, delta));
+        else PB_CUDA(cudaMemsetAsync(ny.A, 0, ny.r * ny.lda * sizeof(double), st));
+        if (ny.ncols > 0) {
+            PB_TRY(gram_cross(st, prob->kernel, ny.Zl, ny.r, ws.Z() + d.lo, ny.ncols, Df, ny.r, n, ny.G, ny.ldg, s + d.lo));
+            PB_TRY(gemm_nt(st, ny.r, ny.r, ny.ncols, 1.0, ny.G, ny.ldg, ny.G, ny.ldg, 1.0, ny.A, ny.lda, true));
+        }
+        PB_TRY(comm_allreduce_sum(d.comm, st, ny.A, ny.r * ny.lda));
+    } else {
+        dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), 64), (unsigned)ny.r);
+        nystrom_prep_kernel<<<grid, 256, 0, st>>>(ws.K(), ld, s, n, ny.r, ny.stride, delta, ny.G, ny.A, ny.lda); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+        PB_TRY(gemm_nt(st, ny.r, ny.r, n, 1.0, ny.G, ld, ny.G, ld, 1.0, ny.A, ny.lda, true));
+    }
     PB_TRY(potrf(st, ny.A, ny.r, ny.lda, ny.pws, ny.pws_bytes, info));
     int32_t info_host = 0;
     PB_CUDA(cudaMemcpyAsync(&info_host, info, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -682,6 +657,27 @@ int nystrom_pcg(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, con
     const int64_t ld = ws.L.ld;
     const int splits = gemv_t_splits(ny.r);
     auto precondition = [&](double* rz_slot) -> int {      // z = r - G^T A^{-1} G r ; rz = r.z
+        if (ws.dist) {
+            // column-sharded G: t = sum over ranks of G_q r_q (all-reduce of r doubles), the r x r solves are
+            // replicated, z_q = r_q - G_q^T t is local, one all-gather returns z; r.z is then taken on the full
+            // (replicated) vectors so every rank computes bit-identical CG scalars
+            const DistCtx& d = *ws.dist;
+            const unsigned nbl = vec_blocks(ny.ncols);
+            if (ny.ncols > 0) PB_TRY(gemv(st, ny.G, ny.r, ny.ncols, ny.ldg, ws.vec(V_R) + d.lo, ny.t));
+            else PB_CUDA(cudaMemsetAsync(ny.t, 0, ny.r * sizeof(double), st));
+            PB_TRY(comm_allreduce_sum(d.comm, st, ny.t, ny.r));
+            PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, false, ny.t, ny.u));
+            PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, true, ny.u, ny.t));
+            if (ny.ncols > 0) {
+                PB_TRY(gemv_t_partial(st, ny.G, ny.r, ny.ncols, ny.ldg, ny.t, ny.gt, ny.ldg));
+                nystrom_z_kernel<<<nbl, 256, 0, st>>>(ws.vec(V_R) + d.lo, ny.gt, splits, ny.ldg, ny.ncols, ws.vec(V_Z) + d.lo,
+                                                      ws.partial()); pb::note_launch();
+            }
+            PB_TRY(comm_allgather(d.comm, st, ws.vec(V_Z), d.nloc_max));
+            dot2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_R), ws.vec(V_Z), ws.vec(V_R), ws.vec(V_Z), n, ws.partial()); pb::note_launch();
+            PB_CUDA(cudaGetLastError());
+            return finalize(st, ws, nb, rz_slot, nullptr);
+        }
         PB_TRY(gemv(st, ny.G, ny.r, n, ld, ws.vec(V_R), ny.t));
         PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, false, ny.t, ny.u));
         PB_TRY(trsv(st, ny.A, ny.r, ny.lda, ny.pws, true, ny.u, ny.t));
@@ -702,26 +698,42 @@ bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
 // of the factor-every-step iterates (eta = 1e-1: 1.6e-10; eta <= 1e-3: 1.7e-11, the FP64 floor).
 double cg_target(const pb_problem* prob, double tolerance) { return opt_cg_tol() * tolerance * prob->lik.sigma; }
 
+// Smallest curvature W = -h accepted as "zero" (pb_options.negative_curvature_tol, in units of 1/sigma^2).
+double curvature_floor(const pb_problem* prob) {
+    return -opts().negative_curvature_tol / (prob->lik.sigma * prob->lik.sigma);
+}
+
 }  // namespace
+
+// ---- small helpers shared with dist.cu ----
+// s = sqrt(max(p, 0)) into V_S; the count of materially negative / NaN precisions lands in the S_BAD scalar
+int precision_sqrt(cudaStream_t st, const Ws& ws, const pb_problem* prob, const double* precision) {
+    const unsigned nb = vec_blocks(prob->n);
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, prob->n, curvature_floor(prob), ws.vec(V_S), ws.partial()); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return finalize(st, ws, nb, nullptr, ws.scalars() + S_BAD);
+}
+
+// var[i] = kss - ||V[i, :]||^2
+int row_sumsq(cudaStream_t st, const double* V, int64_t rows, int64_t cols, int64_t ld, double kss, double* var) {
+    if (rows <= 0) return PB_OK;
+    row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, st>>>(V, rows, cols, ld, kss, var); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int64_t dist_nystrom_doubles(int64_t n, int64_t nloc_max, int Dfmax) {
+    Nystrom ny;
+    ny.r = nystrom_rank(n);
+    if (ny.r <= 0) return 0;
+    return nystrom_carve(ny, nullptr, n, round_up(n > 0 ? n : 1, 16), nloc_max, Dfmax, true);
+}
+
 }  // namespace pb
 
 using namespace pb;
 
 extern "C" int64_t pb_fit_workspace_bytes(int64_t n, int D) { return make_layout(n, D).total; }
-
-extern "C" int pb_set_factor_callback(pb_factor_fn fn, void* user) {
-    std::lock_guard<std::mutex> lock(g_factor_mu);
-    g_factor_fn = fn;
-    g_factor_user = user;
-    return PB_OK;
-}
-
-extern "C" int pb_set_matvec_callback(pb_matvec_fn fn, void* user) {
-    std::lock_guard<std::mutex> lock(g_factor_mu);
-    g_matvec_fn = fn;
-    g_matvec_user = user;
-    return PB_OK;
-}
 
 extern "C" int pb_build_gram(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes) {
     Ws ws;
@@ -747,11 +759,20 @@ extern "C" int pb_workspace_gram(void* workspace, int64_t n, int D, double** K, 
 extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
                               double jitter, int32_t final_factor, void* workspace, int64_t workspace_bytes,
                               double* weight, double* precision, double* posterior_mean,
-                              pb_fit_result* result_host) {
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+                              pb_fit_result* result_host, const pb_options* options) {
+    OptScope opt_scope(options);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
+    return laplace_fit_impl(reinterpret_cast<cudaStream_t>(stream), prob, tolerance, maxiter, jitter, final_factor, ws,
+                            weight, precision, posterior_mean, result_host);
+}
+
+int pb::laplace_fit_impl(cudaStream_t st, const pb_problem* prob, double tolerance, int32_t maxiter, double jitter,
+                         int32_t final_factor, Ws& ws, double* weight, double* precision, double* posterior_mean,
+                         pb_fit_result* result_host) {
+    const bool sharded = ws.dist != nullptr;
     PB_CHECK(weight && precision && result_host, PB_ERR_INVALID, "laplace_fit: null output");
+    PB_CHECK(!(sharded && final_factor), PB_ERR_INVALID, "laplace_fit: the sharded fit leaves the factorisation to pb_dist_predict");
     lik::Params lp;
     PB_TRY(lik::make_params(prob->lik, lp));
     const int64_t n = prob->n, ld = ws.L.ld;
@@ -760,6 +781,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
 
     PB_TRY(build_gram(st, prob, ws));
     PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    PB_CUDA(cudaMemsetAsync(ws.info(), 0, 256, st));        // potrf is the only other writer: a CG-only fit must not read a stale word
     PB_CUDA(cudaMemsetAsync(ws.vec(V_W), 0, n * sizeof(double), st));       // z_init = zeros (approximators.py:268)
 
     double host[S_COUNT];
@@ -771,13 +793,16 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
     bool have_factor = false;
     // Newton steps by Nystrom-preconditioned CG (no factorisation) until it fails once, then the factor path
     Nystrom ny;
-    if (pcg_enabled(n) && prob->lik.kind != PB_LIK_GAUSSIAN) ny = nystrom_layout(ws, n);
+    if (sharded || (pcg_enabled(n) && prob->lik.kind != PB_LIK_GAUSSIAN)) ny = nystrom_layout(ws, n);
     bool nystrom_live = ny.r > 0, nystrom_warm = false;
+    // The sharded fit has no replicated factor to fall back on: its Newton steps are Nystrom-CG only.
+    PB_CHECK(!sharded || nystrom_live, PB_ERR_UNSUPPORTED,
+             "laplace_fit (multi-GPU): the Nystrom preconditioner is disabled or does not fit (n = %lld too small?)", (long long)n);
     while (error > tolerance && it < maxiter) {                             // jaxopt loop (solvers.py:13-14)
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
         else PB_TRY(K_times(st, ws, n, w, ws.vec(V_F), nystrom_live && !have_factor ? ny.symv : nullptr));
-        laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, ws.vec(V_S),
-                                                ws.vec(V_B), ws.partial()); pb::note_launch();
+        laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, curvature_floor(prob),
+                                                ws.vec(V_S), ws.vec(V_B), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
         PB_TRY(K_times(st, ws, n, ws.vec(V_B), ws.vec(V_T), nystrom_live && !have_factor ? ny.symv : nullptr));   // K b
@@ -806,7 +831,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
             // delta regularises a numerically rank-deficient landmark block (EQ kernels: cond(K_II) > 1e16).  M is
             // SPD for any delta >= 0; delta perturbs the approximated K by ~(n/r) delta, i.e. the preconditioned
             // spectrum by (n/r) delta W ~ 0.04, while keeping cond(A) <~ 1e8.
-            PB_TRY(nystrom_build(st, ws, ny, n, ws.vec(V_S), 1e-3 * prob->kernel.scale, &ok));
+            PB_TRY(nystrom_build(st, ws, ny, n, ws.vec(V_S), 1e-3 * prob->kernel.scale, &ok, prob));
             if (ok) PB_TRY(nystrom_pcg(st, ws, ny, n, ws.vec(V_S), ws.vec(V_C), 150, cg_target(prob, tolerance), nystrom_warm, &used));
             if (used >= 0) {
                 solved = true;
@@ -817,6 +842,8 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
                 nystrom_live = false;
             }
         }
+        PB_CHECK(solved || !sharded, PB_ERR_NUMERIC,
+                 "laplace_fit (multi-GPU): Nystrom-preconditioned CG did not reach its target at Newton iteration %d", it + 1);
         if (!solved) {
             PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));
             PB_CUDA(cudaMemcpyAsync(ws.vec(V_SF), ws.vec(V_S), n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -833,8 +860,8 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         result_host->iterations = it;
         result_host->info = info_host;
         if (host[S_BAD] > 0) {
-            set_error("laplace_fit: %d data have negative or NaN likelihood curvature at iteration %d; the SPD "
-                      "Newton form needs W = -h >= 0", (int)host[S_BAD], it);
+            set_error("laplace_fit: %d data have materially negative (< %.3g) or NaN likelihood curvature at iteration %d; "
+                      "the SPD Newton form needs W = -h >= 0", (int)host[S_BAD], curvature_floor(prob), it);
             return PB_ERR_NUMERIC;
         }
         if (info_host != 0) {
@@ -858,7 +885,7 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
         // chol(K + diag(1/p) + jitter I) of objective_LA (Laplace.py:24) in its B form:
         // sum log diag L_cov + 0.5 sum log p == sum log diag chol(I + s s^T o (K + jitter I))
         const unsigned nb2 = vec_blocks(n);
-        sqrt_kernel<<<nb2, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial()); pb::note_launch();
+        sqrt_kernel<<<nb2, 256, 0, st>>>(precision, n, curvature_floor(prob), ws.vec(V_S), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb2, nullptr, ws.scalars() + S_BAD));
         PB_TRY(factor_B(st, ws, n, ws.vec(V_S), jitter));
@@ -879,7 +906,8 @@ extern "C" int pb_laplace_fit(pb_stream_t stream, const pb_problem* prob, double
 
 extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tolerance, int32_t maxiter,
                          void* workspace, int64_t workspace_bytes, double* weight, double* precision,
-                         double* posterior_mean, pb_fit_result* result_host) {
+                         double* posterior_mean, pb_fit_result* result_host, const pb_options* options) {
+    OptScope opt_scope(options);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
@@ -893,6 +921,7 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
 
     PB_TRY(build_gram(st, prob, ws));
     PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    PB_CUDA(cudaMemsetAsync(ws.info(), 0, 256, st));
     // L = chol(sigma^2 I + K) (VB.py:10) — loop invariant, factored once (no jitter: raw-array path)
     PB_TRY(factor_matrix(st, ws, n, nullptr, sigma * sigma, 0.0));
     PB_TRY(logdet_chol(st, ws.B(), n, ld, ws.scalars() + S_LOGDET));
@@ -946,7 +975,8 @@ extern "C" int pb_vb_fit(pb_stream_t stream, const pb_problem* prob, double tole
 
 extern "C" int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, const double* precision,
                                   int32_t reuse_gram, void* workspace, int64_t workspace_bytes,
-                                  int32_t* info_host) {
+                                  int32_t* info_host, const pb_options* options) {
+    OptScope opt_scope(options);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
@@ -954,8 +984,9 @@ extern "C" int pb_predict_prepare(pb_stream_t stream, const pb_problem* prob, co
     const int64_t n = prob->n;
     if (!reuse_gram) PB_TRY(build_gram(st, prob, ws));
     PB_CUDA(cudaMemsetAsync(ws.scalars(), 0, S_COUNT * sizeof(double), st));
+    PB_CUDA(cudaMemsetAsync(ws.info(), 0, 256, st));
     const unsigned nb = vec_blocks(n);
-    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, ws.vec(V_S), ws.partial()); pb::note_launch();
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, curvature_floor(prob), ws.vec(V_S), ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, nullptr, ws.scalars() + S_BAD));
     PB_TRY(factor_B(st, ws, n, ws.vec(V_S), 0.0));       // K + diag(1/p) (approximators.py:175) in B form
@@ -1025,7 +1056,8 @@ extern "C" int64_t pb_gradient_scratch_bytes(int64_t n) {
 
 extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                                    const double* weight, const double* precision, void* scratch, int64_t scratch_bytes,
-                                   double* grad_host, int32_t grad_len) {
+                                   double* grad_host, int32_t grad_len, const pb_options* options) {
+    OptScope opt_scope(options);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
@@ -1044,7 +1076,7 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
 
     PB_TRY(gemv(st, ws.K(), n, n, ld, weight, f));
     PB_TRY(likelihood(st, prob->lik, f, prob->y, n, 1, nullptr, g, nullptr, d3));
-    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, sv, ws.partial()); pb::note_launch();
+    sqrt_kernel<<<nb, 256, 0, st>>>(precision, n, curvature_floor(prob), sv, ws.partial()); pb::note_launch();
     // b_c * c = K g ;  b_l * l = (K o rho) g
     PB_TRY(gemv(st, ws.K(), n, n, ld, g, ws.vec(V_B)));
     PB_TRY(gram_deriv_matvec(st, prob->kernel, ws.Z(), n, Df, n, ws.K(), ld, g, ws.vec(V_T)));
@@ -1066,7 +1098,8 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     PB_TRY(trsm_right_lt(st, ws.B(), n, ld, ws.potrf_ws(), U, n, ld));
     row_sumsq_kernel<<<(unsigned)ceil_div<int64_t>(n, 8), 256, 0, st>>>(U, n, n, ld, 0.0, ws.vec(V_Q)); pb::note_launch();
     grad_s2_kernel<<<nb, 256, 0, st>>>(ws.vec(V_Q), precision, d3, f, prob->y, gaussian ? 1 : 0, prob->lik.sigma, n,
-                                       ws.vec(V_P), ws.vec(V_E), ws.partial()); pb::note_launch();
+                                       curvature_floor(prob), prob->kernel.scale, ws.vec(V_P), ws.vec(V_E),
+                                       ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, sc + S_GSIG, sc + S_BAD));
     const bool ordinal_params = !gaussian && grad_len >= 3 + prob->lik.J + 1;
@@ -1088,7 +1121,7 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
     double host[S_COUNT];
     PB_TRY(read_scalars(st, ws, host, nullptr));
     if (host[S_BAD] > 0) {
-        set_error("laplace_gradient: %d precisions are not positive (V = (1 - Binv_ii) / W undefined)", (int)host[S_BAD]);
+        set_error("laplace_gradient: %d precisions are materially negative or NaN", (int)host[S_BAD]);
         return PB_ERR_NUMERIC;
     }
     const double c = prob->kernel.scale, l = prob->kernel.stretch_out;
@@ -1115,12 +1148,13 @@ extern "C" int pb_laplace_gradient(pb_stream_t stream, const pb_problem* prob, v
 
 // s = sqrt(-h), W = -h ; partial[1]: number of data with -h < 0 or NaN
 __global__ void __launch_bounds__(256)
-vb_curvature_kernel(const double* __restrict__ h, int64_t n, double* __restrict__ s, double* __restrict__ W,
-                    double* __restrict__ partial) {
+vb_curvature_kernel(const double* __restrict__ h, int64_t n, double neg_floor, double* __restrict__ s,
+                    double* __restrict__ W, double* __restrict__ partial) {
     double bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        const double w = -h[i];
-        if (!(w >= 0.0)) bad += 1.0;
+        double w = -h[i];
+        if (!(w >= neg_floor)) bad += 1.0;
+        w = w > 0.0 ? w : 0.0;
         W[i] = w;
         s[i] = sqrt(w);
     }
@@ -1162,7 +1196,8 @@ vb_gauss_sigma_kernel(const double* __restrict__ f, const double* __restrict__ y
 // the DMMA GEMM.  grad_host layout as pb_laplace_gradient: [d scale, d stretch_out, d sigma, d cutpoint_0..J].
 extern "C" int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* workspace, int64_t workspace_bytes,
                               const double* weight, void* scratch, int64_t scratch_bytes, double* grad_host,
-                              int32_t grad_len) {
+                              int32_t grad_len, const pb_options* options) {
+    OptScope opt_scope(options);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     Ws ws;
     PB_TRY(bind(prob, workspace, workspace_bytes, ws));
@@ -1185,7 +1220,7 @@ extern "C" int pb_vb_gradient(pb_stream_t stream, const pb_problem* prob, void* 
     PB_CUDA(cudaMemsetAsync(sc, 0, S_COUNT * sizeof(double), st));
     PB_TRY(gemv(st, ws.K(), n, n, ld, weight, f));
     PB_TRY(likelihood(st, prob->lik, f, prob->y, n, 1, nullptr, nullptr, ws.vec(V_T), nullptr));
-    vb_curvature_kernel<<<nb, 256, 0, st>>>(ws.vec(V_T), n, sv, Wv, ws.partial()); pb::note_launch();
+    vb_curvature_kernel<<<nb, 256, 0, st>>>(ws.vec(V_T), n, curvature_floor(prob), sv, Wv, ws.partial()); pb::note_launch();
     PB_CUDA(cudaGetLastError());
     PB_TRY(finalize(st, ws, nb, nullptr, sc + S_BAD));
     fill_kernel<<<nb, 256, 0, st>>>(ones, n, 1.0); pb::note_launch();

@@ -349,12 +349,11 @@ int make_map(CUtensorMap* map, const double* base, int64_t rows, int64_t cols, i
 template <class CF>
 int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
            const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
         PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared));
-        configured = true;
     }
     CUtensorMap mapA, mapB;
     PB_TRY(make_map(&mapA, A, M, K, lda, CF::BM));

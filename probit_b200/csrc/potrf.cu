@@ -191,10 +191,9 @@ int trsm_rec(const Ctx& c, double* B, int64_t ldb, int64_t m, const double* L, i
 
 int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
     if (n <= LEAF) {
-        static bool configured = false;
-        if (!configured) {
+        static PerDeviceOnce configured;
+        if (configured.first()) {
             PB_CUDA(cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-            configured = true;
         }
         potrf_leaf_kernel<<<1, 256, LEAF_SMEM, c.stream>>>(A, c.lda, (int)n, c.dinv + (col0 / LEAF) * LEAF * LEAF,
                                                            c.info, (int)col0); pb::note_launch();
@@ -336,10 +335,9 @@ int rebuild_solve_workspace(cudaStream_t stream, const double* L, int64_t n, int
                             int64_t workspace_bytes) {
     PB_CHECK(workspace_bytes >= pb_potrf_workspace_bytes(n), PB_ERR_INVALID, "rebuild_solve_workspace: workspace too small");
     if (n == 0) return PB_OK;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
         PB_CUDA(cudaFuncSetAttribute(leaf_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LEAF_SMEM));
-        configured = true;
     }
     double* dinv = reinterpret_cast<double*>(workspace);
     leaf_inverse_kernel<<<(unsigned)((n + LEAF - 1) / LEAF), 256, LEAF_SMEM, stream>>>(L, n, ldl, dinv); pb::note_launch();
@@ -364,7 +362,8 @@ extern "C" int64_t pb_potrf_workspace_bytes(int64_t n) {
 }
 
 extern "C" int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,
-                        int64_t workspace_bytes, int32_t* info) {
+                        int64_t workspace_bytes, int32_t* info, const pb_options* options) {
+    pb::OptScope opt_scope(options);
     return pb::potrf(reinterpret_cast<cudaStream_t>(stream), A, n, lda, workspace, workspace_bytes, info);
 }
 

@@ -5,10 +5,16 @@ One process per GPU (torchrun), `torch.distributed` for the plumbing:
     an optional all_gather returns the full (mean, variance) on every rank.
   * hyper-parameter / restart batches: independent fits -> restart r runs on rank r mod world; one
     all_gather of the scalar objectives (and gradients) at the end.
-The reference has no distributed code at all; these helpers are the host logic of
-BASELINE configs[4].  They are backend-agnostic (nccl on GPUs; the CPU tests drive them with gloo
-and an injected compute function).
+  * ONE large fit over all the GPUs (`ShardedLaplaceGP`): rows of K sharded for the Newton / CG iterations,
+    block-column-cyclic Cholesky with NCCL panel broadcasts, test points sharded.  All of that runs inside the
+    C ABI (pb_dist_laplace_fit / pb_dist_predict, csrc/dist.cu): the collectives are enqueued on CUDA streams from
+    C++, Python only bootstraps the communicator (128-byte NCCL id through torch.distributed).
+The reference has no distributed code at all; the first two helpers are the host logic of
+BASELINE configs[4] and are backend-agnostic (nccl on GPUs; the CPU tests drive them with gloo and an injected
+compute function).
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -79,249 +85,184 @@ def restart_batch(evaluate_fn, parameter_list, group=None, device=None):
 
 
 # ------------------------------------------------------------------------------------------------
-# Large-N Cholesky across GPUs: 1-D block-column-cyclic, right-looking, one-panel
-# look-ahead, panels broadcast over the process group (NCCL on NVLink/NVSwitch).
-#
-# Why 1-D and not a 2-D grid: on NVSwitch every GPU receives every panel at full link bandwidth, and
-# the whole factorisation moves only 8*N^2/2 bytes per GPU (17 GB at N=65536, ~25 ms at 700 GB/s)
-# against N^3/(3G) flops of trailing update (>= 0.34 s at G=8), so the broadcast volume that a 2-D
-# layout would save is already hidden under the update; the 1-D layout keeps every trailing update a
-# single large DMMA GEMM per owned block column.  Because every rank sees every panel, each rank also
-# assembles the complete factor for free (no gather), after which triangular solves and predict run
-# replicated / sharded over test points.
+# ONE fit across the GPUs (SURVEY.md §8e "large-N Cholesky"; BASELINE configs[3] at 2/4/8 GPUs)
 # ------------------------------------------------------------------------------------------------
-class BlockCyclicCholesky:
-    def __init__(self, n, ops, nb=512, group=None):
-        self.n, self.nb, self.ops, self.group = int(n), int(nb), ops, group
-        self.rank, self.world = _world(group)
-        self.nblk = (self.n + self.nb - 1) // self.nb
-        self.owned = [j for j in range(self.nblk) if j % self.world == self.rank]
-        self.ld_loc = max(len(self.owned), 1) * self.nb
-        self.Aloc = ops.empty(self.n, self.ld_loc)                 # owned block columns, side by side
-        self.P = [ops.empty(self.n, self.nb), ops.empty(self.n, self.nb)]   # double-buffered panel (contiguous)
-
-    def width(self, j):
-        return min(self.nb, self.n - j * self.nb)
-
-    def owner(self, j):
-        return j % self.world
-
-    def local_block(self, j):
-        """View of block column j (rows j0.., its own width) inside the local storage."""
-        jl = j // self.world
-        j0 = j * self.nb
-        return self.Aloc[j0:, jl * self.nb: jl * self.nb + self.width(j)]
-
-    def panel_view(self, k):
-        """(n - k0, nb) contiguous panel buffer; only the first width(k) columns are meaningful."""
-        m = self.n - k * self.nb
-        return self.P[k % 2].reshape(-1)[: m * self.nb].view(m, self.nb)
-
-    def _bcast(self, k):
-        buf = self.panel_view(k)
-        if self.world == 1:
-            return None
-        return dist.broadcast(buf, src=dist.get_global_rank(self.group, self.owner(k)) if self.group is not None
-                              else self.owner(k), group=self.group, async_op=True)
-
-    def _produce(self, k):
-        """Owner only: factor panel k in place (diagonal block + rows below) and pack it for the broadcast."""
-        w = self.width(k)
-        blk = self.local_block(k)
-        info = self.ops.potrf_panel(blk, w)
-        self.panel_view(k)[:, :w].copy_(blk)
-        return info
-
-    def _update(self, j, k, Pk):
-        """Block column j -= P_k[rows >= j0] * P_k[rows of block j]^T."""
-        off = (j - k) * self.nb
-        wj, wk = self.width(j), self.width(k)
-        self.ops.gemm_nt(Pk[off:, :wk], Pk[off: off + wj, :wk], self.local_block(j), alpha=-1.0, beta=1.0)
-
-    def factor(self, fill_block, write_panel):
-        """fill_block(j0, w, out): write rows j0.. of columns [j0, j0+w) of the SPD matrix into `out`.
-        write_panel(k0, w, panel): called on EVERY rank for EVERY factored panel ((n-k0) x w, rows k0..).
-        Returns the list of (k0, info) pairs produced by this rank's panel factorisations."""
-        for j in self.owned:
-            fill_block(j * self.nb, self.width(j), self.local_block(j))
-        infos = []
-        if self.owner(0) == self.rank:
-            infos.append((0, self._produce(0)))
-        work = self._bcast(0)
-        for k in range(self.nblk):
-            if work is not None:
-                work.wait()
-            Pk = self.panel_view(k)
-            write_panel(k * self.nb, self.width(k), Pk[:, : self.width(k)])
-            nxt = k + 1
-            if nxt < self.nblk:
-                if self.owner(nxt) == self.rank:          # look-ahead: next panel first, then ship it
-                    self._update(nxt, k, Pk)
-                    infos.append((nxt * self.nb, self._produce(nxt)))
-                work = self._bcast(nxt)                   # receivers post before their own updates
-            for j in self.owned:
-                if j > k and j != nxt:
-                    self._update(j, k, Pk)
-        return infos
-
-
-class TorchCholeskyOps:
-    """CUDA ops of BlockCyclicCholesky: the product's own C ABI (pb_potrf, pb_trsm_right_lt, pb_gemm_nt)."""
-
-    def __init__(self):
-        from . import _lib, linalg
-        self.lib, self.linalg = _lib.load(), linalg
-        self._ws = None
-
-    def empty(self, rows, cols):
-        return torch.empty((rows, cols), dtype=torch.float64, device="cuda")
-
-    def potrf_panel(self, blk, w):
-        import ctypes as C
-        lib, la = self.lib, self.linalg
-        need = lib.pb_potrf_workspace_bytes(w)
-        if self._ws is None or self._ws.numel() * 8 < need:
-            self._ws = torch.empty(need // 8, dtype=torch.float64, device="cuda")
-        info = torch.zeros(1, dtype=torch.int32, device="cuda")
-        st = la._stream()
-        ld = blk.stride(0)
-        from ._lib import check
-        check(lib.pb_potrf(st, la._ptr(blk), w, ld, la._ptr(self._ws), need, la._ptr(info)))
-        m = blk.shape[0] - w
-        if m > 0:
-            below = blk[w:, :]
-            check(lib.pb_trsm_right_lt(st, la._ptr(blk), w, ld, la._ptr(self._ws), la._ptr(below), m, ld))
-        return info
-
-    def gemm_nt(self, A, B, C_out, alpha, beta):
-        self.linalg.gemm_nt(A, B, C_out, alpha=alpha, beta=beta, lower_only=False)
-
-
-def row_shard(n, rank, world):
-    """Equal-sized (padded) row chunks for an all-gather: returns (lo, hi, chunk); ranks past the end get lo == hi."""
-    chunk = -(-n // world)
-    return min(n, rank * chunk), min(n, (rank + 1) * chunk), chunk
-
-
-def sharded_matvec(local_product, n, group=None, device=None, buffers=None):
-    """y = K x with the rows of K split over the ranks.  `local_product(lo, hi, out)` writes K[lo:hi] @ x into
-    out[:hi - lo]; one all_gather_into_tensor of 8 * chunk bytes per rank returns the same y (length n) everywhere.
-    `buffers` (dict) caches the padded send / receive tensors between calls."""
+def exchange_unique_id(make_id, group=None, device=None):
+    """Rank 0 calls `make_id() -> 128 bytes`; every rank returns the same bytes (one broadcast of a uint8 tensor
+    through torch.distributed: NCCL needs a CUDA tensor, gloo a CPU one — `device` says which)."""
     rank, world = _world(group)
-    lo, hi, chunk = row_shard(n, rank, world)
-    buffers = buffers if buffers is not None else {}
-    if buffers.get("chunk") != (chunk, world):
-        buffers["chunk"] = (chunk, world)
-        buffers["loc"] = torch.zeros(chunk, dtype=torch.float64, device=device)
-        buffers["full"] = torch.zeros(world * chunk, dtype=torch.float64, device=device)
-    loc, full = buffers["loc"], buffers["full"]
-    if hi > lo:
-        local_product(lo, hi, loc)
+    buf = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        raw = make_id()
+        assert len(raw) == 128
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
     if world > 1:
-        dist.all_gather_into_tensor(full, loc, group=group)
-        return full[:n]
-    return loc[:n]
+        src = dist.get_global_rank(group, 0) if group is not None else 0
+        dist.broadcast(buf, src=src, group=group)
+    return bytes(buf.cpu().numpy().tobytes())
 
 
-class DistributedFactorization:
-    """Installs the block-cyclic Cholesky as the factorisation of an approximator's fit / predict drivers
-    (pb_set_factor_callback).  Every rank must run the same fit on the same data (replicas)."""
+class Communicator:
+    """pb_comm: the library's own NCCL communicator (plus its communication / look-ahead streams) on the current
+    CUDA device.  world == 1 needs no NCCL at all."""
 
-    def __init__(self, approximator, group=None, nb=512, shard_matvec=None):
-        """shard_matvec: also replace y = K x of the Newton / CG iterations by a row-sharded product followed by an
-        all-gather (pb_set_matvec_callback); default: whenever the group has more than one rank."""
-        import ctypes as C
-        from . import _lib, linalg
-        self.gp, self.group, self.lib, self.la = approximator, group, _lib.load(), linalg
-        self.chol = BlockCyclicCholesky(approximator.N, TorchCholeskyOps(), nb=nb, group=group)
-        self.calls = 0
-        self.matvec_calls = 0
-        self.shard_matvec = (self.chol.world > 1) if shard_matvec is None else bool(shard_matvec)
-        self._mv_buf = None
+    def __init__(self, group=None):
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world = _world(group)
+        self.group = group
+        handle = C.c_void_p(0)
+        if self.world > 1:
+            def make_id():
+                raw = (C.c_char * 128)()
+                _lib.check(self.lib.pb_comm_unique_id(raw))
+                return bytes(raw)
+            uid = exchange_unique_id(make_id, group, "cuda")
+            _lib.check(self.lib.pb_comm_create(uid, self.rank, self.world, C.byref(handle)))
+        else:
+            _lib.check(self.lib.pb_comm_create(None, 0, 1, C.byref(handle)))
+        self.handle = handle
 
-        def matvec(user, stream, K, n, ldk, x, y):
-            try:
-                self._matvec(K, n, ldk, x, y)
-                return _lib.PB_OK
-            except Exception as exc:
-                self.error = exc
-                return _lib.PB_ERR_CUDA
+    def close(self):
+        if self.handle:
+            self.lib.pb_comm_destroy(self.handle)
+            self.handle = C.c_void_p(0)
 
-        self._mv_cb = _lib.MATVEC_FN(matvec)
-
-        def callback(user, stream, K, n, ldk, s, a, jitter, L, ldl, pws, pws_bytes, info_dev):
-            try:
-                self._factor(K, n, ldk, s, a, jitter, L, ldl, pws, pws_bytes, info_dev)
-                return _lib.PB_OK
-            except Exception as exc:          # never let an exception cross the C boundary
-                self.error = exc
-                return _lib.PB_ERR_CUDA
-
-        self._cb = _lib.FACTOR_FN(callback)
-        self.error = None
-
-    def __enter__(self):
-        import ctypes as C
-        self.lib.pb_set_factor_callback(C.cast(self._cb, C.c_void_p), None)
-        if self.shard_matvec:
-            self.lib.pb_set_matvec_callback(C.cast(self._mv_cb, C.c_void_p), None)
-        return self
-
-    def __exit__(self, *exc):
-        self.lib.pb_set_factor_callback(None, None)
-        self.lib.pb_set_matvec_callback(None, None)
-        return False
-
-    def _matvec(self, K, n, ldk, x, y):
-        """y = K x with the rows of K split evenly over the ranks: each rank streams n/G rows (the product is HBM
-        bound, so this is the 1/G of the time) and one all-gather of 8n bytes puts the same y on every rank."""
-        import ctypes as C
-        lib, la = self.lib, self.la
-
-        def local_product(lo, hi, out):
-            _check(lib.pb_gemv(la._stream(), C.c_void_p(K + lo * ldk * 8), hi - lo, n, ldk, C.c_void_p(x), la._ptr(out)))
-
-        if self._mv_buf is None:
-            self._mv_buf = {}
-        full = sharded_matvec(local_product, n, self.group, "cuda", self._mv_buf)
-        ws = self.gp._workspace()
-        off = y - ws.data_ptr()
-        ws[off: off + n * 8].view(torch.float64).copy_(full)
-        self.matvec_calls += 1
-
-    def _view(self, ptr, rows, ld):
-        ws = self.gp._workspace()
-        off = ptr - ws.data_ptr()
-        return ws[off: off + rows * ld * 8].view(torch.float64).view(rows, ld)
-
-    def _factor(self, K, n, ldk, s, a, jitter, L, ldl, pws, pws_bytes, info_dev):
-        import ctypes as C
-        lib, la = self.lib, self.la
-        st = la._stream()
-        Lv = self._view(L, n, ldl)[:, :n]
-
-        def fill_block(j0, w, out):
-            _check(lib.pb_transform_block(st, C.c_void_p(K), ldk, C.c_void_p(s) if s else None, a, jitter, j0, j0,
-                                          n - j0, w, la._ptr(out), out.stride(0)))
-
-        def write_panel(k0, w, panel):
-            Lv[k0:, k0: k0 + w].copy_(panel)
-
-        infos = self.chol.factor(fill_block, write_panel)
-        glob = torch.zeros(1, dtype=torch.int32, device="cuda")
-        for k0, info in infos:
-            glob = torch.where((glob == 0) & (info > 0), info + k0, glob)
-        if self.chol.world > 1:
-            big = torch.where(glob == 0, torch.full_like(glob, 2**31 - 1), glob)
-            dist.all_reduce(big, op=dist.ReduceOp.MIN, group=self.group)
-            glob = torch.where(big == 2**31 - 1, torch.zeros_like(big), big)
-        ws = self.gp._workspace()
-        off = info_dev - ws.data_ptr()
-        ws[off: off + 4].view(torch.int32).copy_(glob)
-        _check(lib.pb_rebuild_solve_workspace(st, C.c_void_p(L), n, ldl, C.c_void_p(pws), pws_bytes))
-        self.calls += 1
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
-def _check(status):
-    from . import _lib
-    _lib.check(status)
+def _sharded_class():
+    from . import _lib, approximators as _appr
+    from .linalg import _dev, _mat2, _ptr, _stream
+
+    class ShardedLaplaceGP(_appr.LaplaceGP):
+        """LaplaceGP (probit/approximators.py:213-277) for ONE training set partitioned over the ranks of a process
+        group.  Same constructor and methods; every rank passes the SAME data and parameters and receives the same
+        (weight, precision).  `predict` takes this rank's LOCAL test points (shard them with `shard_range`;
+        `predict_global` does that and all-gathers the result).  Memory per GPU is N^2/G for the Gram rows plus
+        N^2/G for the rank's block columns of the factor, so N beyond one GPU's 180 GB fits."""
+
+        def __init__(self, data, prior, log_likelihood, grad_log_likelihood=None, hessian_log_likelihood=None,
+                     comm=None, group=None, **kwargs):
+            super().__init__(data, prior, log_likelihood, grad_log_likelihood, hessian_log_likelihood, **kwargs)
+            self.comm = comm if comm is not None else Communicator(group)
+            self.group = self.comm.group
+            self.rank, self.world = self.comm.rank, self.comm.world
+
+        def __repr__(self):
+            return f"ShardedLaplaceGP(rank {self.rank} of {self.world})"
+
+        def _workspace(self):
+            if self._ws is None:
+                self._ws_bytes = self.lib.pb_dist_workspace_bytes(self.N, self.D, self.world, self.rank, C.byref(self.options))
+                self._ws = torch.empty(self._ws_bytes, dtype=torch.uint8, device="cuda")
+            return self._ws
+
+        def _fit(self, parameters, final_factor):
+            prob, keep = self._problem(parameters)
+            ws = self._workspace()
+            w = torch.empty(self.N, dtype=torch.float64, device="cuda")
+            p = torch.empty_like(w)
+            f = torch.empty_like(w)
+            res = _lib.FitResult()
+            self._gram_key, self._factor_key = None, None
+            status = self.lib.pb_dist_laplace_fit(_stream(), self.comm.handle, C.byref(prob), float(self.tolerance),
+                                                  int(self.maxiter), _ptr(ws), self._ws_bytes, _ptr(w), _ptr(p), _ptr(f),
+                                                  C.byref(res), C.byref(self.options))
+            self.last_result = res
+            _lib.check(status)
+            if final_factor:
+                self.last_logdet = self._factor_predict(prob, p, w, None, float(self.jitter), want_logdet=True)[2]
+            del keep
+            return w, p, f
+
+        def _chunk_rows(self, n_test):
+            if self.predict_chunk:
+                return max(1, min(int(self.predict_chunk), max(n_test, 1)))
+            free, _ = torch.cuda.mem_get_info()
+            budget = min(int(free * 0.7), 64 << 30)
+            ld = (self.N + 15) // 16 * 16
+            return max(1, min(max(n_test, 1), budget // (8 * ld + 16 * self.D + 512)))
+
+        def _factor_predict(self, prob, precision, weight, X_test, jitter, want_logdet=False, variance=True):
+            ws = self._workspace()
+            n_test = 0 if X_test is None else X_test.shape[0]
+            key = (self._spec_key(prob.kernel), float(jitter))
+            reuse = (self._factor_key is not None and self._factor_key[0] == key
+                     and torch.equal(self._factor_key[1], precision) and not want_logdet)
+            chunk = self._chunk_rows(n_test)
+            sbytes = self.lib.pb_dist_predict_scratch_bytes(self.N, self.D, min(chunk, max(n_test, 1))) if n_test else 0
+            scratch = torch.empty(max(sbytes, 256), dtype=torch.uint8, device="cuda")
+            mean = torch.empty(n_test, dtype=torch.float64, device="cuda")
+            var = torch.empty(n_test, dtype=torch.float64, device="cuda") if variance else None
+            logdet, info = C.c_double(float("nan")), C.c_int32(0)
+            self._factor_key = None
+            _lib.check(self.lib.pb_dist_predict(
+                _stream(), self.comm.handle, C.byref(prob), _ptr(precision), _ptr(weight), _ptr(ws), self._ws_bytes,
+                float(jitter), int(reuse), _ptr(X_test) if n_test else None, n_test, chunk, _ptr(scratch), sbytes,
+                _ptr(mean) if n_test else None, _ptr(var) if (variance and n_test) else None,
+                C.byref(logdet) if want_logdet else None, C.byref(info), C.byref(self.options)))
+            if variance or want_logdet:
+                self._factor_key = (key, precision.clone())
+            return mean, var, logdet.value
+
+        def predict(self, X_test, parameters, weight, precision, variance=True):
+            """(mean, variance) at this rank's LOCAL test points (approximators.py:154-180).  Every rank must call
+            it (the panels of the factor are broadcast to all ranks), possibly with zero rows."""
+            prob, keep = self._problem(parameters)
+            weight = _dev(weight).reshape(-1)
+            precision = _dev(precision).reshape(-1)
+            X_test = _mat2(X_test) if X_test is not None and len(X_test) else None
+            if X_test is not None and X_test.shape[1] != self.D:
+                raise ValueError("X_test has the wrong input dimension")
+            mean, var, _ = self._factor_predict(prob, precision, weight, X_test, 0.0, variance=variance)
+            del keep
+            return mean.to(self.out_dtype), (var.to(self.out_dtype) if var is not None else None)
+
+        def predict_global(self, X_test, parameters, weight, precision):
+            """Full-length (mean, variance) on every rank: shard X_test, predict locally, all-gather."""
+            def fn(Xs):
+                return self.predict(Xs, parameters, weight, precision)
+            m, v, _ = predict_sharded(fn, _mat2(X_test), gather=True, group=self.group)
+            return m, v
+
+        def posterior_mean(self, weight, parameters):
+            """K @ weight without a resident K: the fused on-the-fly matvec over this rank's training rows + all-gather."""
+            prob, keep = self._problem(parameters)
+            weight = _dev(weight).reshape(-1)
+
+            def fn(Xs):
+                m = self._factor_predict(prob, torch.ones_like(weight), weight, Xs, 0.0, variance=False)[0]
+                return m, torch.zeros_like(m)
+            m, _, _ = predict_sharded(fn, self.X, gather=True, group=self.group)
+            del keep
+            return m
+
+        def objective(self):
+            """objective_LA (Laplace.py:12-30) with the log-determinant from the block-cyclic factor."""
+            def obj(parameters):
+                self._fit(parameters, final_factor=True)
+                r = self.last_result
+                return -r.sum_ll + 0.5 * r.ftw + self.last_logdet
+            return obj
+
+        def value_and_grad(self):
+            raise NotImplementedError("ShardedLaplaceGP: gradients need the full inverse; run hyper-parameter batches "
+                                      "one per GPU with restart_batch instead (SURVEY.md §8e)")
+
+        def predict_covariance(self, *a, **k):
+            raise NotImplementedError("ShardedLaplaceGP: predict_covariance is single-GPU only")
+
+    return ShardedLaplaceGP
+
+
+def __getattr__(name):
+    if name == "ShardedLaplaceGP":
+        cls = _sharded_class()
+        globals()["ShardedLaplaceGP"] = cls
+        return cls
+    raise AttributeError(name)

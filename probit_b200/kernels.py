@@ -35,8 +35,10 @@ class Kernel:
 
     __radd__ = __add__
 
-    def lower(self):
-        """Flatten the expression tree into a `pb_kernel_spec` (see include/probit_b200.h)."""
+    def lower(self, distance_form=0):
+        """Flatten the expression tree into a `pb_kernel_spec` (see include/probit_b200.h).
+
+        distance_form=1 selects lab's expansion-form squared distance (TEST-ONLY, see the header)."""
         scale, outer, inner, period = 1.0, 1.0, 1.0, None
         node = self
         while True:
@@ -60,8 +62,8 @@ class Kernel:
             else:
                 raise NotImplementedError(f"kernel node {type(node).__name__} is not supported")
         if period is None:
-            return _lib.KernelSpec(base, 0, scale, 1.0, 1.0, outer)
-        return _lib.KernelSpec(base, 1, scale, outer, period, inner)
+            return _lib.KernelSpec(base, 0, scale, 1.0, 1.0, outer, int(distance_form), 0)
+        return _lib.KernelSpec(base, 1, scale, outer, period, inner, int(distance_form), 0)
 
     def __call__(self, x, y=None):
         from . import linalg

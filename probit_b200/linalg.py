@@ -113,14 +113,15 @@ class Factor:
         self.L, self.workspace, self.info = L, workspace, info
 
 
-def potrf_(A, check=True):
+def potrf_(A, check=True, options=None):
     """In-place lower Cholesky of the row-major lower triangle of A. Returns a Factor."""
     lib = _lib.load()
     n = A.shape[0]
     ws_bytes = lib.pb_potrf_workspace_bytes(n)
     ws = torch.empty(ws_bytes // 8, dtype=torch.float64, device="cuda")
     info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    _lib.check(lib.pb_potrf(_stream(), _ptr(A), n, _ld(A), _ptr(ws), ws_bytes, _ptr(info)))
+    _lib.check(lib.pb_potrf(_stream(), _ptr(A), n, _ld(A), _ptr(ws), ws_bytes, _ptr(info),
+                            C.byref(options) if options is not None else None))
     if check:
         i = int(info.item())
         if i != 0:

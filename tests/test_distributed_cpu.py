@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from probit_b200.distributed import predict_sharded, restart_batch, row_shard, sharded_matvec
+from probit_b200.distributed import exchange_unique_id, predict_sharded, restart_batch
 
 
 def _free_port():
@@ -38,6 +38,9 @@ def _worker(rank, world, port, n_test, out):
         full = restart_batch(evaluate, params)
         ok = ok and seen == params[rank::world]
         ok = ok and torch.equal(full, torch.tensor([[p * p, -p] for p in params], dtype=torch.float64))
+        # communicator bootstrap: rank 0's 128 bytes reach every rank (NCCL's unique id travels this way)
+        uid = exchange_unique_id(lambda: bytes(range(128)), device="cpu")
+        ok = ok and uid == bytes(range(128))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
@@ -59,106 +62,84 @@ def test_single_process_paths():
     assert torch.equal(full, torch.tensor([[2.0], [3.0], [4.0]], dtype=torch.float64))
 
 
-# ---- block-cyclic Cholesky host logic (numpy/torch-CPU ops injected) ----------------------------------
-class _CpuOps:
-    def empty(self, rows, cols):
-        return torch.zeros((rows, cols), dtype=torch.float64)
-
-    def potrf_panel(self, blk, w):
-        d = blk[:w, :w]
-        Lc = torch.linalg.cholesky(torch.tril(d) + torch.tril(d, -1).T)
-        blk[:w, :w] = torch.tril(Lc) + torch.triu(d, 1)          # strict upper left as it was
-        if blk.shape[0] > w:
-            blk[w:, :] = torch.linalg.solve_triangular(Lc, blk[w:, :].T, upper=False).T
-        return torch.zeros(1, dtype=torch.int32)
-
-    def gemm_nt(self, A, B, C_out, alpha, beta):
-        C_out.copy_(alpha * (A @ B.T) + beta * C_out)
+# ---- the schedule of csrc/dist.cu (block-column-cyclic Cholesky + test rows carried along), modelled on CPU ----------
+def _spd(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    G = torch.randn(n, n + 3, dtype=torch.float64, generator=g)
+    s = torch.rand(n, dtype=torch.float64, generator=g) + 0.5
+    K = G @ G.T / n
+    B = torch.eye(n, dtype=torch.float64) + s[:, None] * K * s[None, :]
+    return K, s, B
 
 
-def _chol_worker(rank, world, port, n, nb, out):
-    from probit_b200.distributed import BlockCyclicCholesky
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+def _model_worker(rank, world, port, n, nb, out):
+    from bc_model import BlockCyclicModel, make_apply_hook
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        g = torch.Generator().manual_seed(5)
-        G = torch.randn(n, n + 3, dtype=torch.float64, generator=g)
-        A = G @ G.T + n * torch.eye(n, dtype=torch.float64)
-        Lfull = torch.zeros(n, n, dtype=torch.float64)
-        chol = BlockCyclicCholesky(n, _CpuOps(), nb=nb)
-        seen = []
+        K, s, B = _spd(n, 5)
+        g = torch.Generator().manual_seed(7)
+        m_all = 11
+        Ks = torch.randn(m_all, n, dtype=torch.float64, generator=g)            # stand-in for k(X*, X)
+        from probit_b200.distributed import shard_range
+        lo, hi = shard_range(m_all, rank, world)                                  # test points sharded, no collective
+        V = (Ks[lo:hi] * s[None, :]).clone()
+        model = BlockCyclicModel(n, nb)
+        logdet = [0.0]
+        apply = make_apply_hook(V, n)
 
-        def fill(j0, w, o):
-            o.copy_(A[j0:, j0:j0 + w])
+        def hook(k, k0, w, P):
+            logdet[0] += float(torch.log(torch.diagonal(P[:w, :w])).sum())
+            apply(k, k0, w, P)
 
-        def write(k0, w, panel):
-            seen.append(k0)
-            Lfull[k0:, k0:k0 + w] = panel
-
-        chol.factor(fill, write)
-        ref = torch.linalg.cholesky(A)
-        err = (torch.tril(Lfull) - ref).abs().max().item()
-        out[rank] = (err < 1e-10, seen == [k * nb for k in range(chol.nblk)], len(chol.owned))
+        model.factor(lambda i, j: B[i, j], hook)
+        L = torch.linalg.cholesky(B)
+        var = 1.0 - (V * V).sum(1)
+        var_ref = 1.0 - torch.einsum("ij,ij->i", Ks[lo:hi] * s, torch.cholesky_solve((Ks[lo:hi] * s).T, L).T)
+        ok_var = bool(torch.allclose(var, var_ref, rtol=0, atol=1e-10))
+        ok_logdet = abs(logdet[0] - float(torch.log(torch.diagonal(L)).sum())) < 1e-9
+        # owned block columns hold the factor
+        ok_factor = True
+        for j in range(model.me, model.nblk, model.world):
+            j0, w = j * nb, model.width(j)
+            ok_factor = ok_factor and bool(torch.allclose(torch.tril(model.col(j)[:w]), torch.tril(L[j0:j0 + w, j0:j0 + w]), atol=1e-10))
+            ok_factor = ok_factor and bool(torch.allclose(model.col(j)[w:], L[j0 + w:, j0:j0 + w], atol=1e-10))
+        # a later chunk of test rows re-streams the stored panels
+        V2 = (Ks[lo:hi] * s[None, :]).clone()
+        model.stream(make_apply_hook(V2, n))
+        ok_stream = bool(torch.allclose(V2, V, rtol=0, atol=1e-12))
+        recv_order = [k for e, k in model.log if e == "recv"]
+        ok_order = recv_order == list(range(model.nblk)) * 2
+        out[rank] = (ok_var, ok_logdet, ok_factor, ok_stream, ok_order)
     finally:
-        dist.destroy_process_group()
+        if world > 1:
+            dist.destroy_process_group()
 
 
-def test_block_cyclic_cholesky_world2_matches_lapack():
-    world = 2
-    for n, nb in [(37, 8), (64, 16), (50, 64)]:
+def test_block_cyclic_schedule_world2_matches_lapack():
+    for n, nb in [(37, 8), (64, 16), (50, 64), (96, 8)]:
         with mp.Manager() as mgr:
             out = mgr.dict()
-            mp.spawn(_chol_worker, args=(world, _free_port(), n, nb, out), nprocs=world, join=True)
+            mp.spawn(_model_worker, args=(2, _free_port(), n, nb, out), nprocs=2, join=True)
             res = dict(out)
-            assert res[0][:2] == (True, True) and res[1][:2] == (True, True), (n, nb, res)
-            assert res[0][2] + res[1][2] == (n + nb - 1) // nb
+            assert res[0] == (True,) * 5 and res[1] == (True,) * 5, (n, nb, res)
 
 
-def test_block_cyclic_cholesky_single_process():
-    from probit_b200.distributed import BlockCyclicCholesky
-    n, nb = 45, 8
-    G = torch.randn(n, n, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
-    A = G @ G.T + n * torch.eye(n, dtype=torch.float64)
-    Lfull = torch.zeros(n, n, dtype=torch.float64)
-    chol = BlockCyclicCholesky(n, _CpuOps(), nb=nb)
-    chol.factor(lambda j0, w, o: o.copy_(A[j0:, j0:j0 + w]), lambda k0, w, p: Lfull[k0:, k0:k0 + w].copy_(p))
-    assert (torch.tril(Lfull) - torch.linalg.cholesky(A)).abs().max().item() < 1e-10
+def test_block_cyclic_schedule_single_process():
+    out = {}
+    _model_worker(0, 1, 0, 45, 8, out)
+    assert out[0] == (True,) * 5
 
 
-def _matvec_worker(rank, world, port, n, out):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    try:
-        g = torch.Generator().manual_seed(5)
-        K = torch.randn(n, n, dtype=torch.float64, generator=g)
-        K = K + K.T
-        buffers, ok = {}, True
-        for trial in range(3):                                   # buffers are reused between calls
-            x = torch.randn(n, dtype=torch.float64, generator=g)
-            seen = []
-            def local_product(lo, hi, dst):
-                seen.append((lo, hi))
-                dst[: hi - lo] = K[lo:hi] @ x
-            y = sharded_matvec(local_product, n, buffers=buffers)
-            lo, hi, chunk = row_shard(n, rank, world)
-            ok = ok and seen == ([(lo, hi)] if hi > lo else []) and y.numel() == n
-            ok = ok and torch.allclose(y, K @ x, rtol=0, atol=1e-12)
-        out[rank] = bool(ok)
-    finally:
-        dist.destroy_process_group()
-
-
-def test_row_sharded_matvec_world2_ragged():
-    for n in (7, 64):                                            # 7: ragged last shard
-        with mp.Manager() as mgr:
-            out = mgr.dict()
-            mp.spawn(_matvec_worker, args=(2, _free_port(), n, out), nprocs=2, join=True)
-            assert dict(out) == {0: True, 1: True}
-
-
-def test_row_shard_covers_every_row_once():
-    for n in (1, 5, 8, 1000):
-        for world in (1, 2, 3, 8):
-            spans = [row_shard(n, r, world) for r in range(world)]
-            rows = [i for lo, hi, _ in spans for i in range(lo, hi)]
-            assert rows == list(range(n)) and len({c for _, _, c in spans}) == 1
+def test_dist_layout_queries_do_not_need_a_gpu():
+    """pb_dist_workspace_bytes: per-rank memory is ~2 N^2 / G (row block of K + the rank's block columns), so N = 131072
+    fits eight 180 GB GPUs although one N x N matrix alone (128 GiB) plus its factor would not fit one."""
+    from probit_b200 import _lib
+    lib = _lib.load()
+    one = lib.pb_fit_workspace_bytes(131072, 4)
+    per_rank = [lib.pb_dist_workspace_bytes(131072, 4, 8, r, None) for r in range(8)]
+    assert one > 250 * 2**30 and max(per_rank) < 40 * 2**30
+    assert len(set(per_rank)) == 1                                  # same size on every rank (symmetric allocation)
+    assert lib.pb_dist_workspace_bytes(65536, 4, 1, 0, None) < lib.pb_fit_workspace_bytes(65536, 4) + (2 << 30)
+    assert lib.pb_dist_predict_scratch_bytes(65536, 4, 512) >= 512 * 65536 * 8

@@ -26,11 +26,31 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_layouts_match_the_header():
     from probit_b200 import _lib
-    assert ctypes.sizeof(_lib.KernelSpec) == 40
+    assert ctypes.sizeof(_lib.KernelSpec) == 48
     assert ctypes.sizeof(_lib.LikelihoodSpec) == 40
     assert ctypes.sizeof(_lib.FitResult) == 48
-    assert ctypes.sizeof(_lib.Problem) == 32 + 40 + 40
-    assert _lib.Problem.kernel.offset == 32 and _lib.Problem.lik.offset == 72
+    assert ctypes.sizeof(_lib.Options) == 48
+    assert ctypes.sizeof(_lib.Problem) == 32 + 48 + 40
+    assert _lib.Problem.kernel.offset == 32 and _lib.Problem.lik.offset == 80
+
+
+def test_options_are_per_call_not_global():
+    """pb_options replaces the process-global tunables: defaults come from the library, overrides live in the caller's
+    struct, and there is no setter left to mutate shared state (SURVEY.md §8b re-entrancy contract)."""
+    from probit_b200 import _lib
+    lib = _lib.load()
+    o = _lib.default_options()
+    assert (o.laplace_pcg_min_n, o.laplace_nystrom_rank, o.potrf_block, o.potrf_lookahead) == (24576, -1, 0, 1)
+    assert o.laplace_cg_tol == 1e-2 and o.negative_curvature_tol == 1e-6
+    o2 = _lib.default_options(laplace_pcg_min_n=0, dist_block=256)
+    assert o2.laplace_pcg_min_n == 0 and o2.dist_block == 256 and _lib.default_options().laplace_pcg_min_n == 24576
+    assert not hasattr(lib, "pb_set_option") and not hasattr(lib, "pb_set_factor_callback")
+    with pytest.raises(KeyError):
+        _lib.default_options(no_such_option=1)
+    # the panel width is part of the workspace layout, so the size query takes the same options
+    a = lib.pb_dist_workspace_bytes(8192, 4, 2, 0, ctypes.byref(o2))
+    b = lib.pb_dist_workspace_bytes(8192, 4, 2, 0, None)
+    assert a > 0 and b > 0
 
 
 def test_workspace_queries_do_not_need_a_gpu():

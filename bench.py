@@ -1,21 +1,33 @@
 """bench.py — the hot path of BASELINE.json on B200: LaplaceGP ordinal (J=5) approximate_posterior + predict.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload fit|predict|restarts]
 
-A "step" is one full pass of the hot path over the synthetic C4 workload (BASELINE.json configs[3]):
-N=65536, D=4, J=5, Matern12 (l=1, s^2=1), sigma=sqrt(0.4), tol=1e-5, FP64: Gram -> Newton to
-convergence (one Cholesky per iteration) -> precision -> predict (one more Cholesky + N_test-RHS solve)
-at N_test=4096.  `value` times K steps with all inputs resident in HBM; `e2e` times K steps through the
-public class API from pinned HOST buffers (H2D of X, y, X_test and D2H of weight, precision, mean,
-variance inside the timed region).  Multi-GPU (N>1): one hyperparameter restart per GPU (BASELINE
-north_star: "independent hyperparameter or restart batches map one per GPU"), no data-path collective,
-weak scaling; value = max-over-ranks step time / N (seconds per fit+predict at aggregate throughput).
+Default workload `fit` (BASELINE.json configs[3], the configuration `metric` is quoted on): a "step" is ONE full pass
+of the hot path over the synthetic workload N=65536, D=4, J=5, Matern12 (l=1, s^2=1), sigma=sqrt(0.4), tol=1e-5, FP64:
+Gram -> Newton to convergence -> precision -> predict (Cholesky of B(w*) + N_test-RHS solve) at N_test=4096.
+`value` times K steps with all inputs resident in HBM; `e2e` times K steps through the public class API from pinned
+HOST buffers (H2D of X, y, X_test and D2H of weight, precision, mean, variance inside the timed region).
 
-The reference arm (--impl reference) and the cpu_baseline leg time the NumPy/SciPy oracle port in the
-reference's literal operation sequence (dense Jacobian + LU, JAX itself is not installable here) on a
-bounded sample (smaller N) and scale by N^3 — see `sample` in the JSON line.
+Multi-GPU (N>1, one process per GPU under torchrun): the SAME single fit + predict is partitioned over the N GPUs
+(`scaling: "strong"`): rows of K sharded for the Newton / CG iterations (local row-block matvec + all-gather), the
+Nystrom preconditioner split by columns (one r x r all-reduce per Newton step), block-column-cyclic Cholesky with NCCL
+panel broadcasts, test points sharded — every collective enqueued from C++ (probit_b200/csrc/dist.cu).  `value` = the
+max-over-ranks time of that one job.  The throughput of N independent restarts (one per GPU, no collective) is kept
+as the extra key `restarts`.
+
+`--workload predict`  BASELINE configs[4]: predict (mean AND variance) over --test-n test points (default 10^6)
+                      sharded over the GPUs at N=65536 (fit untimed); value = seconds, strong scaling.
+`--workload restarts` BASELINE configs[4]: a --restarts (default 64) lengthscale batch of value_and_grad evaluations,
+                      restart r on GPU r mod N; value = seconds for the batch, strong scaling.
+
+The reference arm (--impl reference) and the cpu_baseline leg time the NumPy/SciPy oracle port in the reference's
+literal operation sequence (dense Jacobian + LU; JAX itself is not installable here) at THREE bounded sizes, fit
+t(N) = a N^2 + b N^3 through them and report the model's value at N=65536 together with the raw points and the
+bracketing extrapolations — see `sample` in the JSON line.
 """
 import argparse
+import ctypes as C
+import glob
 import json
 import os
 import subprocess
@@ -39,15 +51,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--train-n", dest="n", type=int, default=65536, help="training points (65536 = BASELINE config; smaller only for debugging)")
-    ap.add_argument("--test-n", dest="n_test", type=int, default=4096)
-    ap.add_argument("--cpu-sample-n", dest="cpu_n", type=int, default=4096, help="bounded-sample size of the CPU baseline / reference arm")
+    ap.add_argument("--workload", default="fit", choices=["fit", "predict", "restarts"])
+    ap.add_argument("--train-n", dest="n", type=int, default=65536,
+                    help="training points (65536 = BASELINE config; smaller only for debugging)")
+    ap.add_argument("--test-n", dest="n_test", type=int, default=None, help="default 4096 (fit) / 1000000 (predict)")
+    ap.add_argument("--restarts", type=int, default=64)
+    ap.add_argument("--cpu-sample-n", dest="cpu_n", type=int, default=4096,
+                    help="per-step bounded-sample size of the CPU baseline / reference arm (the scan adds N/2 and 2N)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--parallelism", default="restarts", choices=["restarts", "cholesky"],
-                    help="multi-GPU mode: one hyperparameter restart per GPU (weak scaling, default) or ONE fit whose "
-                         "Cholesky factorisations are block-cyclic across the GPUs and whose test points are sharded "
-                         "(strong scaling)")
-    return ap.parse_args()
+    ap.add_argument("--no-comparators", action="store_true", help="skip the potrf / cuSOLVER / cuBLAS side measurements")
+    ap.add_argument("--no-restarts-key", action="store_true", help="N>1: skip the extra independent-restart throughput step")
+    ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"],
+                    help="fit workload at N=1: `single` = LaplaceGP (default), `sharded` = the multi-GPU code path with one rank")
+    a = ap.parse_args()
+    if a.n_test is None:
+        a.n_test = 1000000 if a.workload == "predict" else 4096
+    return a
 
 
 def workload_name(n, n_test):
@@ -79,38 +98,76 @@ def cpu_step(X, y, cut, Xs):
     return len(gp.trace), float(m[0] + v[0])
 
 
-def cpu_sample_info(args, seconds):
-    scale = (args.n / args.cpu_n) ** 3
+def cpu_time_at(n, n_test, reps=1):
+    X, y, cut, Xs = cpu_problem(n, min(n_test, n))
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        cpu_step(X, y, cut, Xs)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def fit_cost_model(points):
+    """Non-negative least squares of t = a N^2 + b N^3 through [(N, seconds)], in relative error (each size weighs the same)."""
+    from scipy.optimize import nnls
+    A = np.array([[n ** 2 / t, n ** 3 / t] for n, t in points])
+    coef, _ = nnls(A, np.ones(len(points)))
+    return float(coef[0]), float(coef[1])
+
+
+def cpu_sample_info(args, points):
+    """points: [(N, seconds)] measured on this host, ascending N.  value = a N^2 + b N^3 at the target N."""
+    n = args.n
+    a, b = fit_cost_model(points)
+    value = a * n ** 2 + b * n ** 3
+    (n0, t0), (n1, t1) = points[0], points[-1]
+    exponent = float(np.log(t1 / t0) / np.log(n1 / n0))
+    lo, hi = t1 * (n / n1) ** exponent, t1 * (n / n1) ** 3
+    raw = ", ".join(f"N={p[0]}: {p[1]:.2f} s" for p in points)
     return {
         "kind": "port",
         "cores": os.cpu_count(),
-        "sample": (f"NumPy/SciPy oracle port, literal reference sequence (dense Jacobian + LU solve per Newton "
-                   f"iteration, LU predict) at N={args.cpu_n}, N_test={min(args.n_test, args.cpu_n)}: "
-                   f"{seconds:.2f} s measured, scaled by (N/{args.cpu_n})^3 = {scale:.0f}x to N={args.n} "
-                   f"(EXTRAPOLATED: the literal path needs 3 NxN buffers = 96 GiB at N=65536); JAX is not installable here"),
-        "measured_seconds": seconds,
-        "value": seconds * scale,
+        "sample": (f"NumPy/SciPy oracle port, literal reference sequence (dense Jacobian + LU solve per Newton iteration, "
+                   f"LU predict), N_test=min({args.n_test}, N), measured at {raw}; log-log slope {exponent:.2f} between "
+                   f"the end points (not yet N^3: Gram rebuilds and memory traffic still weigh at these sizes), so the "
+                   f"figure at N={n} is the least-squares model t = a N^2 + b N^3 (a={a:.3e}, b={b:.3e}) -> {value:.0f} s; "
+                   f"bracket: measured-slope extrapolation from N={n1} {lo:.0f} s ... pure N^3 from N={n1} {hi:.0f} s. "
+                   f"EXTRAPOLATED (the literal path needs 3 NxN buffers = 96 GiB at N=65536); JAX is not installable here"),
+        "points": [{"n": p[0], "seconds": p[1]} for p in points],
+        "model": {"form": "a*N^2 + b*N^3", "a": a, "b": b},
+        "loglog_slope": exponent,
+        "value_range": [lo, hi],
+        "value": value,
         "unit": "s",
     }
 
 
 def run_reference(args):
+    """Reference arm: every step times the literal port at --cpu-sample-n; the N/2 and 2N points of the scan are timed
+    once (the 2N point costs ~4x a step).  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    X, y, cut, Xs = cpu_problem(args.cpu_n, min(args.n_test, args.cpu_n))
+    n_mid = args.cpu_n
+    X, y, cut, Xs = cpu_problem(n_mid, min(args.n_test, n_mid))
     for _ in range(args.warmup):
         cpu_step(X, y, cut, Xs)
-    t0 = time.perf_counter()
+    times = []
     for _ in range(args.steps):
+        t0 = time.perf_counter()
         cpu_step(X, y, cut, Xs)
-    per_step = (time.perf_counter() - t0) / max(args.steps, 1)
-    info = cpu_sample_info(args, per_step)
+        times.append(time.perf_counter() - t0)
+    t_mid = float(np.median(times)) if times else cpu_time_at(n_mid, args.n_test)
+    points = [(n_mid // 2, cpu_time_at(n_mid // 2, args.n_test, reps=2)), (n_mid, t_mid),
+              (n_mid * 2, cpu_time_at(n_mid * 2, args.n_test))]
+    info = cpu_sample_info(args, points)
     line = {
         "impl": "reference", "metric": METRIC, "value": info["value"], "unit": "s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": info["value"] * 1e3, "higher_is_better": False,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.n_test), "parallelism": "host cores (OpenBLAS threads)"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.n, args.n_test), "parallelism": "host cores (OpenBLAS threads)",
+                   "timed_per_step": f"literal port at N={n_mid} (median {t_mid:.2f} s); value is the fitted model at N={args.n}"},
         "cpu_baseline": info,
         "e2e": {"value": info["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -168,48 +225,241 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def run_ours(args):
-    import ctypes as C
-    import torch
-    import torch.distributed as dist
-    from probit_b200 import _lib, approximators as PA, kernels as PK, utilities as PU
+class Env:
+    """Process-group plumbing of one rank."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: probit_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events, max over ranks (ms)."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    def share(self, arrays):
+        """Rank 0's NumPy arrays on every rank (one broadcast each): every rank must see bit-identical inputs."""
+        torch = self.torch
+        out = []
+        for a in arrays:
+            t = torch.as_tensor(np.ascontiguousarray(a)).cuda()
+            if self.world > 1:
+                self.dist.broadcast(t, src=0)
+            out.append(t.cpu().numpy())
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def make_inputs(env, n, n_test):
+    from probit_b200 import kernels as PK
     from probit_b200.datasets import device_latent_sampler, generate_ordinal_data
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: probit_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = _lib.load()
-
-    n, n_test = args.n, args.n_test
     gen_kernel = 1.0 * PK.Matern12().stretch(1.0)                   # examples/classification.py:375
-    X, g, y, cut = generate_ordinal_data(SEED, n, 4, 5, NOISE_VARIANCE, device_latent_sampler(gen_kernel, 1e-6))
+    if env.rank == 0:
+        X, g, y, cut = generate_ordinal_data(SEED, n, 4, 5, NOISE_VARIANCE, device_latent_sampler(gen_kernel, 1e-6))
+    else:
+        X, y, cut = np.zeros((n, 4)), np.zeros(n, dtype=np.int64), np.zeros(6)
+    X, y, cut = env.share([X, y, cut])
     Xs = np.random.default_rng(SEED + 1).uniform(-0.5, 1.5, size=(n_test, 4))
-    torch.cuda.empty_cache()
-    # restart batch: rank r evaluates lengthscale l_r (geometric spread around the generating value 1.0)
-    cholesky_mode = world > 1 and args.parallelism == "cholesky"
-    lengthscale = 1.0 if cholesky_mode else float(2.0 ** ((rank - (world - 1) / 2.0) / 8.0))
-    params = (lengthscale, (float(np.sqrt(NOISE_VARIANCE)), cut))
-    prior = lambda l: 1.0 * PK.Matern12().stretch(l)
+    env.torch.cuda.empty_cache()
+    return X, y, cut, Xs
 
+
+def measure_peak(lib):
+    peak = C.c_double(0)
+    if lib.pb_measure_fp64_tensor_peak(C.byref(peak)) == 0 and peak.value > 0:
+        return peak.value, ("FP64 DMMA register-resident mma.sync.m16n8k8 loop measured in this process on this GPU "
+                            "(pb_measure_fp64_tensor_peak); MEASURED_PEAKS.json carries no FP64 figure")
+    return 37.0, "fallback 37.0 TFLOP/s (profiles/r01_fp64_peaks.json)"
+
+
+# ---- library comparators, bench.py only (the product links neither cuSOLVER nor cuBLAS) ------------------------------
+def _find_lib(stem):
+    import torch
+    roots = [os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia"), "/usr/local/cuda/lib64",
+             "/usr/local/cuda/targets/x86_64-linux/lib"]
+    for r in roots:
+        hits = sorted(glob.glob(os.path.join(r, "**", stem + ".so*"), recursive=True))
+        if hits:
+            return hits[0]
+    return stem + ".so"
+
+
+def cusolver_potrf_tflops(torch, sizes):
+    """cusolverDnXpotrf (64-bit API) on a diagonally dominant SPD matrix, both fill modes, best of the two: the library
+    comparator SURVEY.md §2.1 names.  Returns {n: TFLOP/s}."""
+    out = {}
+    try:
+        for dep in ("libcublasLt", "libcublas", "libcusparse"):
+            try:
+                C.CDLL(_find_lib(dep), mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+        cs = C.CDLL(_find_lib("libcusolver"), mode=C.RTLD_GLOBAL)
+        handle, params = C.c_void_p(), C.c_void_p()
+        assert cs.cusolverDnCreate(C.byref(handle)) == 0
+        assert cs.cusolverDnCreateParams(C.byref(params)) == 0
+        cs.cusolverDnSetStream(handle, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        R64F = 1
+        for n in sizes:
+            A = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            info = torch.zeros(1, dtype=torch.int32, device="cuda")
+            best = float("inf")
+            for uplo in (0, 1):                      # CUBLAS_FILL_MODE_LOWER / UPPER of the column-major view
+                wdev, whost = C.c_size_t(0), C.c_size_t(0)
+                assert cs.cusolverDnXpotrf_bufferSize(handle, params, uplo, C.c_int64(n), R64F, C.c_void_p(A.data_ptr()), C.c_int64(n),
+                                                      R64F, C.byref(wdev), C.byref(whost)) == 0
+                work = torch.empty(max(wdev.value, 8), dtype=torch.uint8, device="cuda")
+                hwork = C.create_string_buffer(max(whost.value, 8))
+                for rep in range(2 if n >= 65536 else 3):
+                    A.fill_(0.25); A.diagonal().fill_(float(n))
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    st = cs.cusolverDnXpotrf(handle, params, uplo, C.c_int64(n), R64F, C.c_void_p(A.data_ptr()), C.c_int64(n), R64F,
+                                             C.c_void_p(work.data_ptr()), wdev, hwork, whost, C.c_void_p(info.data_ptr()))
+                    e1.record(); e1.synchronize()
+                    assert st == 0 and int(info.item()) == 0
+                    if rep >= 1:
+                        best = min(best, e0.elapsed_time(e1))
+                del work
+            out[str(n)] = n ** 3 / 3.0 / best * 1e-9
+            del A
+            torch.cuda.empty_cache()
+        cs.cusolverDnDestroyParams(params)
+        cs.cusolverDnDestroy(handle)
+    except Exception as exc:     # comparator only: its absence must not fail the bench
+        out["error"] = repr(exc)[:200]
+    return out
+
+
+def cublas_dgemm_tflops(torch, n=8192):
+    try:
+        A = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        B = torch.randn((n, n), dtype=torch.float64, device="cuda")
+        Cm = torch.empty_like(A)
+        best = float("inf")
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.mm(A, B, out=Cm); e1.record(); e1.synchronize()
+            if rep >= 1:
+                best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / best * 1e-9
+    except Exception:
+        return None
+
+
+def our_potrf_tflops(torch, lib, sizes, options=None):
+    from probit_b200 import linalg
+    out = {}
+    for n in sizes:
+        A = linalg.empty_matrix(n, n)
+        wsb = lib.pb_potrf_workspace_bytes(n)
+        ws = torch.empty(wsb // 8, dtype=torch.float64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        best = float("inf")
+        for rep in range(2 if n >= 65536 else 3):
+            A.fill_(0.25); A.diagonal().fill_(float(n))
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            st = lib.pb_potrf(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(A.data_ptr()), n, A.stride(0),
+                              C.c_void_p(ws.data_ptr()), wsb, C.c_void_p(info.data_ptr()),
+                              C.byref(options) if options is not None else None)
+            e1.record(); e1.synchronize()
+            assert st == 0 and int(info.item()) == 0
+            if rep >= 1:
+                best = min(best, e0.elapsed_time(e1))
+        out[str(n)] = n ** 3 / 3.0 / best * 1e-9
+        del A, ws
+        torch.cuda.empty_cache()
+    return out
+
+
+def cholesky_of_final_B(torch, lib, gp, precision):
+    """CUDA events around pb_potrf ALONE on B(w*) = I + P^1/2 K P^1/2 of the benchmarked problem (the one factorisation
+    every step performs): the measured Cholesky TFLOP/s of metric #2."""
+    from probit_b200 import linalg
+    n = gp.N
+    K = gp._K_view()
+    s = precision.clamp_min(0).sqrt()
+    A = linalg.empty_matrix(n, n)
+    wsb = lib.pb_potrf_workspace_bytes(n)
+    ws = torch.empty(wsb // 8, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    times = []
+    for rep in range(3):
+        assert lib.pb_scale_sym_plus_identity(st, C.c_void_p(K.data_ptr()), n, K.stride(0), C.c_void_p(s.data_ptr()), 0.0,
+                                              C.c_void_p(A.data_ptr()), A.stride(0)) == 0
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        assert lib.pb_potrf(st, C.c_void_p(A.data_ptr()), n, A.stride(0), C.c_void_p(ws.data_ptr()), wsb,
+                            C.c_void_p(info.data_ptr()), C.byref(gp.options)) == 0
+        e1.record(); e1.synchronize()
+        assert int(info.item()) == 0
+        if rep >= 1:
+            times.append(e0.elapsed_time(e1))
+    del A, ws
+    torch.cuda.empty_cache()
+    ms = min(times)
+    return ms, n ** 3 / 3.0 / ms * 1e-9
+
+
+# ---- workload: fit (default) ------------------------------------------------------------------------------------------
+def bench_fit(args, env):
+    torch = env.torch
+    from probit_b200 import _lib, approximators as PA, kernels as PK, utilities as PU
+    from probit_b200.distributed import shard_range
+    lib = _lib.load()
+    rank, world = env.rank, env.world
+    n, n_test = args.n, args.n_test
+    X, y, cut, Xs = make_inputs(env, n, n_test)
+    params = (1.0, (float(np.sqrt(NOISE_VARIANCE)), cut))
+    prior = lambda l: 1.0 * PK.Matern12().stretch(l)  # noqa: E731
+    sharded = world > 1 or args.mode == "sharded"
+
+    lo, hi = shard_range(n_test, rank, world)              # test points sharded, no collective on the data path
     X_pin = torch.from_numpy(X).pin_memory()
     y_pin = torch.from_numpy(y).pin_memory()
-    Xs_pin = torch.from_numpy(Xs).pin_memory()
+    Xs_pin = torch.from_numpy(np.ascontiguousarray(Xs[lo:hi])).pin_memory()
     Xd, yd, Xsd = X_pin.cuda(), y_pin.cuda(), Xs_pin.cuda()
 
-    gp = PA.LaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
-    hook = None
-    if cholesky_mode:
-        from probit_b200.distributed import DistributedFactorization, shard_range
-        hook = DistributedFactorization(gp)
-        hook.__enter__()
-        lo, hi = shard_range(n_test, rank, world)          # test points sharded, no collective on the data path
-        Xsd = Xsd[lo:hi].contiguous()
-        Xs_pin = Xs_pin[lo:hi].contiguous().pin_memory()
+    if sharded:
+        from probit_b200.distributed import ShardedLaplaceGP
+        gp = ShardedLaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
+    else:
+        gp = PA.LaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
 
     def step_resident():
         w, p = gp.approximate_posterior(params)
@@ -225,33 +475,13 @@ def run_ours(args):
         m, v = gp.predict(xs, params, w, p)
         return w.cpu(), p.cpu(), m.cpu(), v.cpu()
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, out
-
     for _ in range(args.warmup):
         step_resident()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(env.local_rank)
     sampler.start()
     launches0 = lib.pb_launch_count()
     lib.pb_profile_begin()
-    ms_res, out = timed(step_resident, args.steps)
+    ms_res, out = env.timed(step_resident, args.steps)
     n_l, g_ms, g_fl = C.c_longlong(0), C.c_double(0), C.c_double(0)
     lib.pb_profile_end(C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
     launches = lib.pb_launch_count() - launches0
@@ -259,51 +489,77 @@ def run_ours(args):
     iterations = gp.last_result.iterations
     fit_factorizations = gp.last_result.factorizations
     pcg_iterations = gp.last_result.pcg_iterations
-    ms_e2e, out_h = timed(step_e2e, args.steps)
+    # stage split of one more step (device-synchronised wall clock; informational)
+    env.barrier(); t0 = time.perf_counter()
+    w_, p_ = gp.approximate_posterior(params)
+    env.barrier(); t1 = time.perf_counter()
+    gp.predict(Xsd, params, w_, p_)
+    env.barrier(); t2 = time.perf_counter()
+    stages = {"fit_s": t1 - t0, "predict_s": t2 - t1}
+    ms_e2e, out_h = env.timed(step_e2e, args.steps)
 
     h2d = X_pin.numel() * 8 + y_pin.numel() * 8 + Xs_pin.numel() * 8
     d2h = sum(t.numel() * 8 for t in out_h)
     sec_res = ms_res / 1e3 / args.steps
     sec_e2e = ms_e2e / 1e3 / args.steps
-    if hook is not None:
-        hook.__exit__(None, None, None)
-    units = 1 if cholesky_mode else world      # fits completed per step across the job
+    ws_gib = gp._ws_bytes / 2 ** 30
+
+    cholesky = None
+    if not sharded and not args.no_comparators:
+        ms_chol, tf_chol = cholesky_of_final_B(torch, lib, gp, out[1])
+        cholesky = {"n": n, "per_step": fit_factorizations + 1, "flops": n ** 3 / 3.0, "ms": ms_chol, "tflops": tf_chol,
+                    "how": "CUDA events around pb_potrf alone on B(w*) of this problem, best of 2 after a warm-up"}
+
+    # extra key: independent restarts, one per GPU (north_star: "restart batches map one per GPU"), no collective
+    restarts = None
+    if world > 1 and not args.no_restarts_key:
+        del gp
+        torch.cuda.empty_cache()
+        ls = float(2.0 ** ((rank - (world - 1) / 2.0) / 8.0))
+        rp = (ls, params[1])
+        gp1 = PA.LaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
+
+        def restart_step():
+            w, p = gp1.approximate_posterior(rp)
+            return gp1.predict(Xsd, rp, w, p)
+        restart_step()
+        ms_r, _ = env.timed(restart_step, 1)
+        restarts = {"fits_per_step": world, "seconds_per_step": ms_r / 1e3, "seconds_per_fit_aggregate": ms_r / 1e3 / world,
+                    "what": f"{world} independent lengthscale restarts (fit + predict of this rank's {hi - lo} test points), one per GPU"}
+        del gp1
+        torch.cuda.empty_cache()
+    elif not sharded:
+        del gp
+        torch.cuda.empty_cache()
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        return None
 
-    peak, peak_src = 37.0, "fallback 37.0 TFLOP/s (tools/fp64_peak.cu, earlier run)"
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_fp64_peaks.json")) as fh:
-            peak = float(json.load(fh)["dmma_m16n8k8_tflops_w32"])
-            peak_src = ("FP64 DMMA register-resident mma.sync loop measured on this pool's B200 by tools/fp64_peak.cu "
-                        "(profiles/r01_fp64_peaks.json); MEASURED_PEAKS.json carries no FP64 figure")
-    except (OSError, KeyError, ValueError):
-        pass
+    peak, peak_src = measure_peak(lib)
     achieved = g_fl.value / g_ms.value * 1e-9 if g_ms.value > 0 else None
     n_potrf = fit_factorizations + 1           # + the factorisation of B(w*) that predict needs
     line = {
-        "metric": METRIC, "value": sec_res / units, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": sec_res, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": False,
-        "scaling": "strong" if cholesky_mode else "weak",
+        "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
             "workload": workload_name(n, n_test),
-            "parallelism": ("single GPU" if world == 1 else
-                            (f"one fit: block-column-cyclic Cholesky over {world} GPUs (NCCL panel broadcasts), test points sharded"
-                             if cholesky_mode else
-                             f"restarts: one hyperparameter restart per GPU x{world}, no data-path collective")),
+            "parallelism": ("single GPU" if world == 1 and not sharded else
+                            f"ONE fit + predict partitioned over {world} GPU(s): rows of K sharded (gemv + ncclAllGather per product), "
+                            f"Nystrom build split by columns (ncclAllReduce), block-column-cyclic Cholesky (ncclBroadcast of panels), "
+                            f"test points sharded; all collectives enqueued from C++"),
             "newton_iterations": iterations, "cholesky_per_step": n_potrf, "pcg_iterations_per_step": pcg_iterations,
             "newton_policy": ("Nystrom-preconditioned CG (no factorisation)" if fit_factorizations == 0 else
                               "Cholesky of B, then PCG on the stale factor" if pcg_iterations else "Cholesky of B every step"),
-            "l2": "inputs larger than L2 (K and the factor are 32 GiB each)",
+            "l2": "inputs larger than L2 (K and the factor are 32 GiB in total across the job)",
             "data_generator": "classification.py:181-322 recipe, numpy default_rng(1); latent draw by the product's own Gram + potrf",
+            "workspace_gib_per_gpu": ws_gib,
         },
-        "e2e": {"value": sec_e2e / units, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": sec_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "stages": stages,
         "roofline": {
             "bound": "tensor", "kernel": "gemm_nt_kernel<128x64, 8 warps, 2 CTA/SM> (Cholesky trailing update / TRSM / predict solve)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
@@ -312,18 +568,146 @@ def run_ours(args):
                                                 "tensor-bound, launches in the timed region vary in shape"),
             "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
             "algorithmic_flops_per_step": g_fl.value / args.steps,
+            "note": "rank 0's launches" if world > 1 else None,
         },
-        "cholesky": {"n": n, "per_step": n_potrf, "flops_each": n ** 3 / 3.0,
-                     "tflops_lower_bound": n_potrf * n ** 3 / 3.0 / sec_res * 1e-12},
     }
+    if cholesky is not None:
+        cholesky["frac_of_fp64_tensor_peak"] = cholesky["tflops"] / peak
+        line["cholesky"] = cholesky
+    if restarts is not None:
+        line["restarts"] = restarts
+    if world == 1 and not args.no_comparators:
+        sizes = [16384, 32768] + ([65536] if n >= 65536 else [])
+        line["comparators"] = {
+            "what": "library kernels on the same GPU in the same process (dlopen in bench.py only; the product links neither)",
+            "potrf_tflops_ours": our_potrf_tflops(torch, lib, sizes),
+            "potrf_tflops_cusolverDnDpotrf": cusolver_potrf_tflops(torch, sizes),
+            "cublas_dgemm_8192_tflops": cublas_dgemm_tflops(torch),
+            "fp64_tensor_peak_tflops": peak,
+        }
     if not args.no_cpu_baseline and world == 1:
-        Xc, yc, cutc, Xsc = cpu_problem(args.cpu_n, min(n_test, args.cpu_n))
-        t0 = time.perf_counter()
-        cpu_step(Xc, yc, cutc, Xsc)
-        line["cpu_baseline"] = cpu_sample_info(args, time.perf_counter() - t0)
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        pts = [(m, cpu_time_at(m, n_test)) for m in (args.cpu_n // 2, args.cpu_n, args.cpu_n * 2)]
+        line["cpu_baseline"] = cpu_sample_info(args, pts)
+    return line
+
+
+# ---- workload: predict (BASELINE configs[4]) --------------------------------------------------------------------------
+def bench_predict(args, env):
+    torch = env.torch
+    from probit_b200 import _lib, kernels as PK, utilities as PU
+    from probit_b200.distributed import ShardedLaplaceGP, shard_range
+    lib = _lib.load()
+    rank, world = env.rank, env.world
+    n, n_test = args.n, args.n_test
+    X, y, cut, _ = make_inputs(env, n, 1)
+    params = (1.0, (float(np.sqrt(NOISE_VARIANCE)), cut))
+    prior = lambda l: 1.0 * PK.Matern12().stretch(l)  # noqa: E731
+    lo, hi = shard_range(n_test, rank, world)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(SEED + 1)
+    Xs_pin = (torch.rand((n_test, 4), dtype=torch.float64, device="cuda", generator=gen)[lo:hi] * 2.0 - 0.5).cpu().pin_memory()
+    Xsd = Xs_pin.cuda()
+    gp = ShardedLaplaceGP((X, y), prior, PU.log_probit_likelihood, tolerance=1e-5)
+    w, p = gp.approximate_posterior(params)           # untimed: this workload measures predict
+    gp.predict(Xsd[: min(hi - lo, 4096)], params, w, p)   # factor B(w*) once (cached for the timed calls) + warm-up
+
+    def step_resident():
+        return gp.predict(Xsd, params, w, p)
+
+    def step_e2e():
+        m, v = gp.predict(Xs_pin.cuda(non_blocking=True), params, w, p)
+        return m.cpu(), v.cpu()
+
+    for _ in range(max(args.warmup - 1, 0)):
+        step_resident()
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    launches0 = lib.pb_launch_count()
+    lib.pb_profile_begin()
+    ms_res, out = env.timed(step_resident, args.steps)
+    n_l, g_ms, g_fl = C.c_longlong(0), C.c_double(0), C.c_double(0)
+    lib.pb_profile_end(C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
+    launches = lib.pb_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_e2e, out_h = env.timed(step_e2e, args.steps)
+    m, v = out
+    ok = bool(torch.isfinite(m).all()) and bool(torch.isfinite(v).all()) and float(v.min()) > 0 and float(v.max()) <= 1.0 + 1e-9
+    if rank != 0:
+        return None
+    peak, peak_src = measure_peak(lib)
+    sec = ms_res / 1e3 / args.steps
+    flops = float(n) * n * n_test                      # the variance solve: N^2 flops per test point
+    achieved = g_fl.value / g_ms.value * 1e-9 if g_ms.value > 0 else None
+    return {
+        "metric": f"predict (mean + variance) seconds over {n_test} test points at N={n} FP64", "value": sec, "unit": "s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res / args.steps,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: predict over {n_test} test points sharded over {world} GPU(s), N={n}, D=4, "
+                               f"Matern12, J=5 LaplaceGP posterior; factor of B(w*) resident block-column-cyclic, panels re-streamed per chunk",
+                   "chunk_rows": gp._chunk_rows(hi - lo), "l2": "inputs larger than L2", "variance_in_(0,1]": ok},
+        "e2e": {"value": ms_e2e / 1e3 / args.steps, "unit": "s", "h2d_bytes_per_step": Xs_pin.numel() * 8,
+                "d2h_bytes_per_step": sum(t.numel() * 8 for t in out_h)},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "test_points_per_s": n_test / sec, "solve_tflops_aggregate": flops / sec * 1e-12,
+        "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (right-TRSM + trailing GEMM of the test rows against each panel)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                     "traffic": None, "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
+                     "note": "rank 0's launches"},
+    }
+
+
+# ---- workload: restarts (BASELINE configs[4]) --------------------------------------------------------------------------
+def bench_restarts(args, env):
+    torch = env.torch
+    from probit_b200 import _lib, approximators as PA, kernels as PK, utilities as PU
+    from probit_b200.distributed import restart_batch
+    lib = _lib.load()
+    rank, world = env.rank, env.world
+    n, R = args.n, args.restarts
+    X, y, cut, _ = make_inputs(env, n, 1)
+    sigma = float(np.sqrt(NOISE_VARIANCE))
+    prior = lambda l: 1.0 * PK.Matern12().stretch(l)  # noqa: E731
+    gp = PA.LaplaceGP((X, y), prior, PU.log_probit_likelihood, tolerance=1e-5)
+    vg = gp.value_and_grad()
+    thetas = [float(t) for t in np.geomspace(0.25, 4.0, R)]          # examples/classification.py:489-503 sweeps the lengthscale
+
+    def evaluate(theta):
+        value, (g_prior, g_lik) = vg((theta, (sigma, cut)))
+        return [value, float(g_prior), float(g_lik[0])]
+
+    def step():
+        return restart_batch(evaluate, thetas, device="cuda")
+
+    evaluate(thetas[rank % R])                                         # warm-up: one evaluation per rank
+    launches0 = lib.pb_launch_count()
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    ms, table = env.timed(step, args.steps)
+    clocks = sampler.stop()
+    launches = lib.pb_launch_count() - launches0
+    if rank != 0:
+        return None
+    sec = ms / 1e3 / args.steps
+    tab = table.cpu().numpy()
+    best = int(np.argmin(tab[:, 0]))
+    return {
+        "metric": f"{R}-restart objective+gradient batch seconds at N={n} FP64", "value": sec, "unit": "s", "n_gpus": world,
+        "steps": args.steps, "warmup": 1, "ms_per_step": ms / args.steps, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[4]: {R} lengthscales in [0.25, 4] (geometric), LaplaceGP.value_and_grad each (Newton fit + "
+                               f"Cholesky of B + closed-form implicit gradient), restart r on GPU r mod {world}, one all_gather of the scalars",
+                   "n": n, "l2": "inputs larger than L2"},
+        "gpu_launches": int(launches), "clocks": clocks, "seconds_per_restart": sec * world / R,
+        "best": {"lengthscale": thetas[best], "objective": float(tab[best, 0])},
+        "finite": bool(np.isfinite(tab).all()),
+    }
+
+
+def run_ours(args):
+    env = Env()
+    line = {"fit": bench_fit, "predict": bench_predict, "restarts": bench_restarts}[args.workload](args, env)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    env.close()
 
 
 if __name__ == "__main__":

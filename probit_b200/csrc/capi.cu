@@ -19,15 +19,20 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_profiling{0};
 static std::mutex g_prof_mu;
-struct GemmRec { cudaEvent_t e0, e1; double flops; };
+struct GemmRec { cudaEvent_t e0, e1; double flops; long long launches; };
 static std::vector<GemmRec> g_gemm;
+static thread_local CaptureTally* tl_tally = nullptr;
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 bool profiling_enabled() { return g_profiling.load(std::memory_order_relaxed) != 0; }
-void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops) {
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
-    g_gemm.push_back({e0, e1, flops});
+    g_gemm.push_back({e0, e1, flops, launches});
 }
+void set_capture_tally(CaptureTally* t) { tl_tally = t; }
+CaptureTally* capture_tally() { return tl_tally; }
 
 // Tunables: immutable defaults + a per-thread pointer to the options of the driver call in flight.
 static pb_options default_options() {
@@ -38,7 +43,7 @@ static pb_options default_options() {
     o.negative_curvature_tol = 1e-6;
     o.potrf_block = 0;
     o.potrf_lookahead = 1;
-    o.potrf_graph = 1;
+    o.potrf_graph = 0;                 // measured slower than eager issue on B200: opt-in
     o.dist_block = 0;
     return o;
 }
@@ -79,7 +84,9 @@ extern "C" int pb_profile_end(long long* gemm_launches, double* gemm_ms, double*
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
-    if (gemm_launches) *gemm_launches = (long long)pb::g_gemm.size();
+    long long launches = 0;
+    for (auto& r : pb::g_gemm) launches += r.launches;
+    if (gemm_launches) *gemm_launches = launches;
     if (gemm_ms) *gemm_ms = ms;
     if (gemm_flops) *gemm_flops = fl;
     pb::g_gemm.clear();

@@ -17,8 +17,15 @@ void set_error(const char* fmt, ...);
 // profiling hooks (capi.cu): every kernel launch of the library is counted; when profiling is on the
 // trailing-update GEMM launches are bracketed by CUDA events on their own stream.
 void note_launch();
+void note_launches(long long n);
+long long launch_count();
 bool profiling_enabled();
-void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops);
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches = 1);
+// While a factorisation is being captured into a CUDA graph the GEMM launcher cannot time its launches with events;
+// it adds their algorithmic flops to the capturing thread's tally instead (potrf.cu attributes them to the replay).
+struct CaptureTally { double flops = 0; long long launches = 0; };
+void set_capture_tally(CaptureTally* t);
+CaptureTally* capture_tally();
 
 // Tunables (capi.cu).  There is no mutable global configuration: an extern "C" driver installs the caller's
 // pb_options for the duration of its call on the calling thread (OptScope); everything below it reads them here.

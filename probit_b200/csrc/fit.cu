@@ -542,8 +542,8 @@ struct Nystrom {
 int64_t nystrom_rank(int64_t n) {
     long long r = opt_nystrom_rank();
     if (r < 0) r = std::min<long long>(4096, std::max<long long>(256, n / 16));
-    r = std::min<long long>(std::min<long long>(r, n / 4), 32768) / 256 * 256;     // grid.y of nystrom_prep_kernel
-    return r;
+    r = std::min<long long>(std::min<long long>(r, n / 4), 32768);                 // grid.y of nystrom_prep_kernel
+    return r >= 256 ? r / 256 * 256 : r / 64 * 64;                                 // small n (tests, sharded toy sizes): 64-granular
 }
 
 // Layout inside the (idle) factor region.  Returns the doubles used; `base` may be null (size query).

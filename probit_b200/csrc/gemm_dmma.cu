@@ -373,7 +373,12 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
         blocks = (int64_t)tm * tn;
     }
     PB_CHECK(blocks < (1ll << 31), PB_ERR_INVALID, "gemm_nt: too many tiles");
-    const bool prof = profiling_enabled() && CF::BM == 128;
+    bool prof = profiling_enabled() && CF::BM == 128;
+    const double algorithmic = lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K;
+    if (CaptureTally* tally = capture_tally()) {      // being captured into a graph: no events, tally the flops
+        if (CF::BM == 128) { tally->flops += algorithmic; tally->launches += 1; }
+        prof = false;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof) {
         PB_CUDA(cudaEventCreate(&e0));
@@ -385,7 +390,7 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, stream));
         // algorithmic flops: 2MNK, or the lower triangle N(N+1)K for the SYRK form
-        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K);
+        profile_gemm(e0, e1, algorithmic);
     }
     PB_CUDA(cudaGetLastError());
     return PB_OK;

@@ -258,10 +258,8 @@ bool lookahead_enabled() { return opt_lookahead(); }
 //   main stream : trailing SYRK of step k restricted to the columns right of panel k+1
 //   side stream : (a) update of panel k+1's block column with panel k, (b) factorisation of panel k+1
 // so the latency-bound panel chain (leaf kernels, small GEMMs) runs underneath the big SYRK.
-int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
-          int32_t* info) {
-    PB_CHECK(n >= 0 && lda >= n, PB_ERR_INVALID, "potrf: bad n/lda");
-    PB_CHECK(workspace_bytes >= pb_potrf_workspace_bytes(n), PB_ERR_INVALID, "potrf: workspace too small");
+static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_t n, int64_t lda, void* workspace,
+                       int32_t* info) {
     PB_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), stream));
     if (n == 0) return PB_OK;
     const int64_t NB = potrf_block_size(n);
@@ -282,11 +280,9 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
         return build_block_inverses(stream, A, n, lda, cm.dinv);
     }
 
-    cudaStream_t side;
-    PB_TRY(side_stream(&side));
     Ctx cs{side, lda, reinterpret_cast<double*>(workspace), info};
     EventPool pool;
-    cudaEvent_t ev_panel, ev_trail = nullptr, ev_start;
+    cudaEvent_t ev_panel, ev_trail = nullptr;
 
     // panel 0 on the main stream
     {
@@ -296,7 +292,6 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
         PB_TRY(pool.get(&ev_panel));
         PB_CUDA(cudaEventRecord(ev_panel, stream));
     }
-    (void)ev_start;
     for (int64_t k0 = 0; k0 + NB < n; k0 += NB) {
         const int64_t nb = NB;                       // panel k is full width here (there are rows below it)
         const int64_t k1 = k0 + nb;                  // first row/col of panel k+1
@@ -329,6 +324,147 @@ int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspac
     }
     PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
     return build_block_inverses(stream, A, n, lda, cm.dinv);
+}
+
+// ---- CUDA-graph replay of the factorisation's launch DAG ----
+// One factorisation is 10^2 .. 10^4 small dependent launches on two streams (N = 16384: ~4 k, each with two
+// cuTensorMapEncodeTiled calls on the host); issued eagerly the host falls behind the GPU for N <~ 32768 and the
+// panel chain stalls on launch latency.  The DAG depends only on (A, n, lda, workspace, info, block size,
+// look-ahead), and the drivers call potrf with the SAME buffers step after step (caller-owned workspaces), so the
+// second call with a given key captures the two streams into a graph (capture on an internal stream: the caller's
+// may be the legacy default stream, which cannot be captured) and every later call is ONE cudaGraphLaunch.
+namespace {
+
+struct GraphKey {
+    int dev;
+    const void *A, *ws, *info;
+    int64_t n, lda;
+    int nb, lookahead;
+    bool operator==(const GraphKey& o) const {
+        return dev == o.dev && A == o.A && ws == o.ws && info == o.info && n == o.n && lda == o.lda && nb == o.nb &&
+               lookahead == o.lookahead;
+    }
+};
+
+struct GraphEntry {
+    GraphKey key{};
+    cudaGraphExec_t exec = nullptr;
+    double gemm_flops = 0;            // algorithmic flops of the main-config GEMM launches inside (profiling hook)
+    long long gemm_launches = 0, launches = 0;
+    unsigned long long stamp = 0;
+    bool used = false;
+};
+
+constexpr int GRAPH_SLOTS = 16;
+std::mutex g_graph_mu;
+GraphEntry g_graphs[GRAPH_SLOTS];
+unsigned long long g_graph_clock = 0;
+constexpr int64_t GRAPH_MIN_N = 512;     // below this a factorisation is a handful of launches
+
+int capture_stream(cudaStream_t* out) {
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    int dev = 0;
+    PB_CUDA(cudaGetDevice(&dev));
+    PB_CHECK(dev >= 0 && dev < 64, PB_ERR_INVALID, "device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    if (!streams[dev]) PB_CUDA(cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking));
+    *out = streams[dev];
+    return PB_OK;
+}
+
+}  // namespace
+
+int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
+          int32_t* info) {
+    PB_CHECK(n >= 0 && lda >= n, PB_ERR_INVALID, "potrf: bad n/lda");
+    PB_CHECK(workspace_bytes >= pb_potrf_workspace_bytes(n), PB_ERR_INVALID, "potrf: workspace too small");
+    cudaStream_t side;
+    PB_TRY(side_stream(&side));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (stream != nullptr && stream != cudaStreamLegacy && stream != cudaStreamPerThread)
+        cudaStreamIsCapturing(stream, &cap);                 // the caller is capturing us into ITS graph: just issue
+    if (!opts().potrf_graph || n < GRAPH_MIN_N || cap != cudaStreamCaptureStatusNone)
+        return potrf_eager(stream, side, A, n, lda, workspace, info);
+
+    GraphKey key{};
+    PB_CUDA(cudaGetDevice(&key.dev));
+    key.A = A; key.ws = workspace; key.info = info; key.n = n; key.lda = lda;
+    key.nb = potrf_block_size(n); key.lookahead = lookahead_enabled() ? 1 : 0;
+
+    std::unique_lock<std::mutex> lock(g_graph_mu);
+    GraphEntry* hit = nullptr;
+    GraphEntry* victim = &g_graphs[0];
+    for (GraphEntry& e : g_graphs) {
+        if (e.used && e.key == key) { hit = &e; break; }
+        if (!e.used) { if (victim->used) victim = &e; }
+        else if (victim->used && e.stamp < victim->stamp) victim = &e;
+    }
+    if (!hit) {
+        // first sighting of this key: remember it and run eagerly (one-shot callers never pay for an instantiation)
+        if (victim->exec) { cudaGraphExecDestroy(victim->exec); }
+        *victim = GraphEntry{};
+        victim->key = key;
+        victim->used = true;
+        victim->stamp = ++g_graph_clock;
+        lock.unlock();
+        return potrf_eager(stream, side, A, n, lda, workspace, info);
+    }
+    hit->stamp = ++g_graph_clock;
+    if (!hit->exec) {
+        cudaStream_t cs;
+        PB_TRY(capture_stream(&cs));
+        // every >48 KB kernel attribute must be set before capture starts: one eager factorisation already ran (above)
+        CaptureTally tally;
+        PB_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        set_capture_tally(&tally);
+        const long long launches0 = launch_count();
+        const int rc = potrf_eager(cs, side, A, n, lda, workspace, info);
+        const long long launched = launch_count() - launches0;
+        set_capture_tally(nullptr);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        if (rc != PB_OK || ce != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            hit->used = false;                               // do not try again with this key
+            lock.unlock();
+            if (rc != PB_OK) return rc;
+            return potrf_eager(stream, side, A, n, lda, workspace, info);
+        }
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) {
+            cudaGetLastError();
+            hit->used = false;
+            lock.unlock();
+            return potrf_eager(stream, side, A, n, lda, workspace, info);
+        }
+        hit->exec = exec;
+        hit->gemm_flops = tally.flops;
+        hit->gemm_launches = tally.launches;
+        hit->launches = launched;
+        note_launches(-launched);                            // capture issued nothing; replays are counted below
+    }
+    cudaGraphExec_t exec = hit->exec;
+    const double flops = hit->gemm_flops;
+    const long long gl = hit->gemm_launches, nl = hit->launches;
+    lock.unlock();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    const bool prof = profiling_enabled() && gl > 0;
+    if (prof) {
+        PB_CUDA(cudaEventCreate(&e0));
+        PB_CUDA(cudaEventCreate(&e1));
+        PB_CUDA(cudaEventRecord(e0, stream));
+    }
+    PB_CUDA(cudaGraphLaunch(exec, stream));
+    note_launches(nl);
+    if (prof) {
+        PB_CUDA(cudaEventRecord(e1, stream));
+        profile_gemm(e0, e1, flops, gl);                     // whole replay: GEMMs + leaves + gaps (a lower bound on the GEMM rate)
+    }
+    return PB_OK;
 }
 
 int rebuild_solve_workspace(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, void* workspace,

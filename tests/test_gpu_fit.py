@@ -372,8 +372,17 @@ def test_expansion_distance_form_closes_the_matern12_gap(name):
     assert relerr(w.cpu().numpy(), ref["weight"]) < TOL and relerr(p.cpu().numpy(), ref["precision"]) < TOL
     m, v = gp.predict(g["Xs"], params, w, p)
     assert relerr(m.cpu().numpy(), ref["mean"]) < TOL and relerr(v.cpu().numpy(), ref["variance"]) < TOL
-    cov = gp.predict_covariance(g["Xs"], params, w, p)
-    assert relerr(cov.cpu().numpy(), ref["covariance"]) < TOL
+    cov = gp.predict_covariance(g["Xs"], params, w, p).cpu().numpy()
+    # Off the diagonal the covariance matches at 1e-8 too.  ON the diagonal of K(X*, X*) the reference evaluates
+    # exp(-sqrt(max(r_ii, 1e-30))) where r_ii = ||a||^2 + ||a||^2 - 2 a.a is whatever rounding residue ITS matmul and ITS
+    # row-norm reduction leave (0 or a few 1e-16, i.e. 0 or ~1.5e-8 after the square root: 2.98e-8 on one test point of
+    # the binary fixture); the residue depends on the BLAS summation order and is not reproducible by any other
+    # implementation of the same formula (this kernel's a.a and ||a||^2 round identically, residue exactly 0), so the
+    # diagonal is held to that floor instead.
+    d = cov - ref["covariance"]
+    off = d - np.diag(np.diag(d))
+    assert np.linalg.norm(off) < TOL * np.linalg.norm(ref["covariance"])
+    assert np.abs(np.diag(d)).max() < 5e-8
     assert abs(gp.objective()(params) - float(ref["objective"])) < TOL * abs(float(ref["objective"]))
 
 

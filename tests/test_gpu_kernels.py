@@ -71,6 +71,46 @@ def test_potrf_matches_lapack(n):
     assert relerr(Xd.cpu().numpy(), ref) < 1e-10
 
 
+@pytest.mark.parametrize("n", [700, 3000, 5000])
+def test_potrf_graph_replay_is_bitwise_identical_to_eager(n):
+    """pb_options.potrf_graph: the first call with a given set of buffers runs eagerly, the second captures the two-stream
+    launch DAG into a CUDA graph, later calls replay it.  All of them must produce the same bits as the eager path
+    (same kernels, same order), report failures through `info` the same way, and count the same launches."""
+    torch = _torch()
+    import ctypes as C
+    from probit_b200 import linalg, _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n, 40))
+    A = torch.as_tensor(G @ G.T + np.eye(n), device="cuda")
+    Ad = linalg.empty_matrix(n, n)
+    wsb = lib.pb_potrf_workspace_bytes(n)
+    ws = torch.empty(wsb // 8, dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def run(options):
+        Ad.copy_(A)
+        ws.zero_()
+        n0 = lib.pb_launch_count()
+        _lib.check(lib.pb_potrf(st, C.c_void_p(Ad.data_ptr()), n, Ad.stride(0), C.c_void_p(ws.data_ptr()), wsb,
+                                C.c_void_p(info.data_ptr()), C.byref(options)))
+        torch.cuda.synchronize()
+        return torch.tril(Ad).clone(), ws.clone(), int(info.item()), lib.pb_launch_count() - n0
+
+    eager = run(_lib.default_options(potrf_graph=0))
+    graph_opt = _lib.default_options(potrf_graph=1)
+    for call in range(4):                                   # eager (first sighting), capture + replay, replay, replay
+        L, w, i, launches = run(graph_opt)
+        assert i == 0 and torch.equal(L, eager[0]) and torch.equal(w, eager[1]), call
+        assert launches == eager[3], (call, launches, eager[3])
+    assert relerr(eager[0].cpu().numpy(), np.linalg.cholesky(A.cpu().numpy())) < 1e-12
+    # a replayed graph still reports a non-SPD matrix
+    A[n // 2, n // 2] = -1.0
+    L, w, i, _ = run(graph_opt)
+    assert i == n // 2 + 1
+
+
 def test_potrf_reports_first_bad_pivot():
     torch = _torch()
     from probit_b200 import linalg, _lib

@@ -46,7 +46,7 @@ if "potrf" in which:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             lib.pb_potrf(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(A.data_ptr()), n, A.stride(0),
-                         C.c_void_p(ws.data_ptr()), wsb, C.c_void_p(info.data_ptr()))
+                         C.c_void_p(ws.data_ptr()), wsb, C.c_void_p(info.data_ptr()), None)
             e1.record(); e1.synchronize()
             best = min(best, e0.elapsed_time(e1))
         assert int(info.item()) == 0

@@ -13,12 +13,12 @@ torch.cuda.empty_cache()
 gp = PA.LaplaceGP((torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()), lambda l: 1.0 * PK.Matern12().stretch(l),
                   PU.log_probit_likelihood, tolerance=1e-5)
 params = (1.0, (float(np.sqrt(0.4)), cut))
-_lib.set_option("laplace_pcg_min_n", 1 << 40)
+gp.options.laplace_pcg_min_n = 1 << 40
 w0, p0 = gp.approximate_posterior(params)
 print("factor every step: newton", gp.last_result.iterations, "error", gp.last_result.error, flush=True)
-_lib.set_option("laplace_pcg_min_n", 0)
+gp.options.laplace_pcg_min_n = 0
 for tol in (1e-1, 1e-2, 1e-3, 1e-4):
-    _lib.set_option("laplace_cg_tol", tol)
+    gp.options.laplace_cg_tol = tol
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); w, p = gp.approximate_posterior(params); e1.record(); e1.synchronize()
@@ -26,5 +26,3 @@ for tol in (1e-1, 1e-2, 1e-3, 1e-4):
     print("tol %.0e: fit %.0f ms, newton %d, potrf %d, cg %d, weight rel diff %.2e, precision rel diff %.2e, final error %.3e" % (
         tol, e0.elapsed_time(e1), r.iterations, r.factorizations, r.pcg_iterations,
         ((w - w0).norm() / w0.norm()).item(), ((p - p0).norm() / p0.norm()).item(), r.error), flush=True)
-_lib.set_option("laplace_cg_tol", 1e-2)
-_lib.set_option("laplace_pcg_min_n", 24576)

@@ -19,7 +19,7 @@ for fam, ell in (("matern12", 1.0), ("matern12", 0.25), ("matern12", 4.0), ("eq"
                       PU.log_probit_likelihood, tolerance=1e-5)
     params = (ell, (float(np.sqrt(0.4)), cut))
     for r in ranks:
-        _lib.set_option("laplace_nystrom_rank", r)
+        gp.options.laplace_nystrom_rank = r
         best = 1e30
         for rep in range(2):
             torch.cuda.synchronize()
@@ -31,6 +31,5 @@ for fam, ell in (("matern12", 1.0), ("matern12", 0.25), ("matern12", 4.0), ("eq"
         print(fam, ell, "rank", r, "fit ms %.1f" % best, "newton", res.iterations, "potrf", res.factorizations, "cg", res.pcg_iterations, flush=True)
     del gp
     torch.cuda.empty_cache()
-_lib.set_option("laplace_nystrom_rank", -1)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "newton_sweep.json"), "w"), indent=1)

@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-restarts-key", action="store_true", help="N>1: skip the extra independent-restart throughput step")
     ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"],
                     help="fit workload at N=1: `single` = LaplaceGP (default), `sharded` = the multi-GPU code path with one rank")
+    ap.add_argument("--dist-block", type=int, default=0, help="panel width of the multi-GPU block-cyclic factorisation (0 = auto)")
     a = ap.parse_args()
     if a.n_test is None:
         a.n_test = 1000000 if a.workload == "predict" else 4096
@@ -457,7 +458,8 @@ def bench_fit(args, env):
 
     if sharded:
         from probit_b200.distributed import ShardedLaplaceGP
-        gp = ShardedLaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
+        gp = ShardedLaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5,
+                              options=dict(dist_block=args.dist_block))
     else:
         gp = PA.LaplaceGP((Xd, yd), prior, PU.log_probit_likelihood, tolerance=1e-5)
 

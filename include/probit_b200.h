@@ -90,9 +90,11 @@ typedef struct pb_options {
                                      [256, 4096]; 0 = off (factor once, reuse the stale factor as preconditioner) */
     double laplace_cg_tol;        /* eta: a CG Newton solve stops once the error it leaves in the step is
                                      <= eta * tolerance; default 1e-2 (floor: 1e-15 relative residual) */
-    double negative_curvature_tol; /* W = -h may be slightly negative where Z << eps (utilities.py:57); values in
-                                     [-tol / sigma^2, 0) are treated as 0, anything below (or NaN) is PB_ERR_NUMERIC;
-                                     default 1e-6 */
+    double negative_curvature_tol; /* W = -h is negative where Z <~ eps (utilities.py:57 is not log-concave there); values in
+                                     [-tol / sigma^2, 0) are treated as 0; anything below sends that Newton step through the
+                                     signed Cholesky M = L diag(I, -I) L^T of D + S K S (single GPU), which follows the
+                                     reference's LU step whenever K^-1 + W is positive definite and reports
+                                     PB_ERR_NUMERIC otherwise; default 1e-6 */
     int32_t potrf_block;          /* Cholesky panel width, 0 = auto */
     int32_t potrf_lookahead;      /* 0/1, default 1 */
     int32_t potrf_graph;          /* 1: replay the factorisation's launch DAG from a cached CUDA graph (second and later

@@ -51,7 +51,7 @@ finalize_kernel(const double* __restrict__ partial, int nblk, double* out0, doub
 __global__ void __launch_bounds__(256)
 laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
                     const void* __restrict__ y, int64_t n, double neg_floor, double* __restrict__ s,
-                    double* __restrict__ b, double* __restrict__ partial) {
+                    double* __restrict__ b, double* __restrict__ Wout, double* __restrict__ partial) {
     __shared__ double sc[lik::SMEM_DOUBLES];
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, bad = 0;
@@ -59,14 +59,16 @@ laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double*
         const double fi = f[i];
         const lik::Out o = lik::eval(p, fi, y, i, sc);
         double W = -o.h;
-        // log(Z + 1e-10) is not log-concave where Z << 1e-10 (far tails): h there is ~ +1e-9, which the
-        // reference's LU Newton step simply carries along.  The SPD form treats that datum as W = 0 for this
-        // step (same fixed point: the step solves a slightly different linearisation); only a materially
-        // negative or NaN curvature is an error.
+        // log(Z + 1e-10) is not log-concave where Z <~ 1e-10 (a datum 5.5 .. 8.7 sigma outside its interval): h is
+        // positive there, ~1e-9 in the far tail and up to ~9 / sigma^2 around Z ~ eps.  The reference's LU Newton step
+        // simply carries such data along.  Here: a curvature in [neg_floor, 0) is treated as 0 (same fixed point, the
+        // step solves a marginally different linearisation); anything below keeps its sign and sends the step down
+        // the signed-Cholesky path (indefinite_newton_solve).  `bad` counts those data (NaN included).
         if (!(W >= neg_floor)) bad += 1.0;
-        W = W > 0.0 ? W : 0.0;
-        s[i] = sqrt(W);
+        else W = W > 0.0 ? W : 0.0;
+        s[i] = sqrt(W > 0.0 ? W : 0.0);
         b[i] = fma(W, fi, o.g);
+        Wout[i] = W;
         sum_ll += o.ll;
     }
     write_partials(sum_ll, bad, partial);
@@ -689,6 +691,186 @@ int nystrom_pcg(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, con
     return pcg_run(st, ws, n, s, c, maxit, tol, warm, iters, precondition, ny.symv);
 }
 
+// Smallest curvature W = -h accepted as "zero" (pb_options.negative_curvature_tol, in units of 1/sigma^2).
+double curvature_floor(const pb_problem* prob) {
+    return -opts().negative_curvature_tol / (prob->lik.sigma * prob->lik.sigma);
+}
+
+// ---- Newton step with indefinite curvature: signed Cholesky ----
+// With W = S D S, S = |W|^1/2, D = diag(+-1):   (I + W K)^-1 = I - S (D + S K S)^-1 S K   (for D = I this is the B form).
+// M = D + S K S is symmetric indefinite.  Order the data with non-negative curvature first (p of them, stable) and
+// those with negative curvature last (m):
+//     M = [ B+   E^T ]      B+ = I + S+ K++ S+  (SPD),     M = L diag(I_p, -I_m) L^T,   L = [ L+    0  ]
+//         [ E    C0  ]      C0 = -I + S- K-- S-                                              [ Y^T  Lc ]
+// with L+ L+^T = B+, Y^T = E L+^-T and Lc Lc^T = Y^T Y - C0 = I - S- Sigma-- S-, Sigma = (K^-1 + W+)^-1.  The last
+// matrix is SPD exactly when the full Hessian K^-1 + W is positive definite, i.e. when the Newton step the reference
+// takes with its LU solve (solvers.py:24) is a step towards a minimum; otherwise the second potrf reports it.  Every
+// piece is an existing kernel (potrf, right-TRSM, SYRK, trsv, gemv) on a permuted matrix generated from permuted
+// features; p is made even with a decoupled dummy row so that the second block stays 16-byte aligned for TMA.
+// Cost: one N^3/3 factorisation for that Newton step — the rare path (small sigma or far-out cutpoints).
+__global__ void __launch_bounds__(1024)
+partition_kernel(const double* __restrict__ W, int64_t n, double neg_floor, long long* __restrict__ perm,
+                 long long* __restrict__ counts) {
+    __shared__ long long cnt[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t lo = min(n, (int64_t)t * chunk), hi = min(n, lo + chunk);
+    long long c = 0;
+    for (int64_t i = lo; i < hi; ++i) c += (W[i] >= neg_floor) ? 1 : 0;
+    cnt[t] = c;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        const long long v = t >= off ? cnt[t - off] : 0;
+        __syncthreads();
+        cnt[t] += v;
+        __syncthreads();
+    }
+    const long long p = cnt[1023], pe = p + (p & 1);
+    long long pos = cnt[t] - c, neg = lo - pos;
+    for (int64_t i = lo; i < hi; ++i) {
+        if (W[i] >= neg_floor) perm[pos++] = i;
+        else perm[pe + neg++] = i;
+    }
+    if (t == 0) {
+        if (p & 1) perm[p] = -1;         // dummy: s = 0, unit diagonal, decoupled
+        counts[0] = p;
+        counts[1] = pe;
+    }
+}
+
+// permuted copies: features, sp = |W|^1/2, cp = sp o t   (index -1 = the dummy row)
+__global__ void __launch_bounds__(256)
+gather_perm_kernel(const long long* __restrict__ perm, int64_t np, const double* __restrict__ W, const double* __restrict__ t,
+                   const double* __restrict__ Z, int64_t ldz, int Df, double* __restrict__ Zp, int64_t ldzp,
+                   double* __restrict__ sp, double* __restrict__ cp) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < np; i += (int64_t)gridDim.x * 256) {
+        const long long idx = perm[i];
+        const double sv = idx >= 0 ? sqrt(fabs(W[idx])) : 0.0;
+        sp[i] = sv;
+        cp[i] = idx >= 0 ? sv * t[idx] : 0.0;
+        for (int d = 0; d < Df; ++d) Zp[d * ldzp + i] = idx >= 0 ? Z[d * ldz + idx] : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_perm_kernel(const long long* __restrict__ perm, int64_t np, const double* __restrict__ xp, double* __restrict__ x) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < np; i += (int64_t)gridDim.x * 256) {
+        const long long idx = perm[i];
+        if (idx >= 0) x[idx] = xp[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+abs_sqrt_kernel(const double* __restrict__ a, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = sqrt(fabs(a[i]));
+}
+
+// A[i][i] += delta for i0 <= i < i1
+__global__ void __launch_bounds__(256)
+diag_add_kernel(double* __restrict__ A, int64_t ld, int64_t i0, int64_t i1, double delta) {
+    for (int64_t i = i0 + blockIdx.x * 256ll + threadIdx.x; i < i1; i += (int64_t)gridDim.x * 256) A[i * ld + i] += delta;
+}
+
+// lower triangle of the m x m block: A <- -A
+__global__ void __launch_bounds__(256)
+negate_lower_kernel(double* __restrict__ A, int64_t ld, int64_t m) {
+    const int64_t r = blockIdx.x;
+    for (int64_t c = threadIdx.x; c <= r; c += 256) A[r * ld + c] = -A[r * ld + c];
+}
+
+__global__ void __launch_bounds__(256)
+scale_kernel(const double* __restrict__ a, double alpha, int64_t n, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = alpha * a[i];
+}
+
+__global__ void fold_info2_kernel(int32_t* __restrict__ info, const int32_t* __restrict__ info2, int32_t offset) {
+    if (*info == 0 && *info2 != 0) *info = *info2 + offset;
+}
+
+// x (V_C, original order) = (D + S K S)^-1 (S o t), t = K b in V_T, signed W in V_G; V_S <- |W|^1/2.
+// Overwrites the factor region, both potrf workspaces and the PCG vector slots.
+int indefinite_newton_solve(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
+    const int64_t n = prob->n;
+    const int Df = feature_dim(prob->kernel, prob->D);
+    const unsigned nb = vec_blocks(n + 1);
+    long long* perm = reinterpret_cast<long long*>(ws.vec(V_U));
+    long long* counts = reinterpret_cast<long long*>(ws.info() + 8);
+    partition_kernel<<<1, 1024, 0, st>>>(ws.vec(V_G), n, curvature_floor(prob), perm, counts); pb::note_launch();
+    long long host_counts[2] = {0, 0};
+    PB_CUDA(cudaMemcpyAsync(host_counts, counts, sizeof(host_counts), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(cudaStreamSynchronize(st));
+    const int64_t p = host_counts[0], pe = host_counts[1], np = n + (pe - p), m = np - pe;
+    const int64_t ldm = round_up(np, 16);
+    PB_CHECK(np * ldm <= ws.L.B_doubles, PB_ERR_INVALID, "indefinite Newton step: workspace too small");
+    double *M = ws.B(), *Zp = ws.Zp(), *sp = ws.vec(V_SF);
+    double *rhs = ws.vec(V_R), *z = ws.vec(V_Z), *tmp = ws.vec(V_E), *tx = ws.vec(V_X);
+    gather_perm_kernel<<<nb, 256, 0, st>>>(perm, np, ws.vec(V_G), ws.vec(V_T), ws.Z(), n, Df, Zp, np, sp, rhs); pb::note_launch();
+    abs_sqrt_kernel<<<nb, 256, 0, st>>>(ws.vec(V_G), n, ws.vec(V_S)); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    // M = I + sp sp^T o K[perm, perm] from the permuted features, then -2 on the diagonal of the negative block
+    PB_TRY(gram_block(st, prob->kernel, Zp, np, Df, 0, np, 0, np, sp, 1.0, 0.0, M, ldm));
+    if (m > 0) {
+        diag_add_kernel<<<(unsigned)std::min<int64_t>(ceil_div<int64_t>(m, 256), 1024), 256, 0, st>>>(M, ldm, pe, np, -2.0); pb::note_launch();
+        PB_CUDA(cudaGetLastError());
+    }
+    const int64_t pws_bytes = pb_potrf_workspace_bytes(n + 1);
+    double* Yt = M + pe * ldm;            // m x pe
+    double* Cb = Yt + pe;                 // m x m
+    int32_t* info2 = ws.info() + 3;
+    if (pe > 0) PB_TRY(potrf(st, M, pe, ldm, ws.potrf_ws(), pws_bytes, ws.info()));
+    else PB_CUDA(cudaMemsetAsync(ws.info(), 0, sizeof(int32_t), st));
+    if (m > 0) {
+        if (pe > 0) {
+            PB_TRY(trsm_right_lt(st, M, pe, ldm, ws.potrf_ws(), Yt, m, ldm));
+            PB_TRY(gemm_nt(st, m, m, pe, 1.0, Yt, ldm, Yt, ldm, -1.0, Cb, ldm, true));          // Y^T Y - C0
+        } else {
+            negate_lower_kernel<<<(unsigned)m, 256, 0, st>>>(Cb, ldm, m); pb::note_launch();
+            PB_CUDA(cudaGetLastError());
+        }
+        PB_TRY(potrf(st, Cb, m, ldm, ws.potrf_ws2(), pws_bytes, info2));
+        fold_info2_kernel<<<1, 1, 0, st>>>(ws.info(), info2, (int32_t)pe); pb::note_launch();
+    }
+    // L z = c ; z2 <- -z2 ; L^T x = z
+    const double* dinv1 = reinterpret_cast<const double*>(ws.potrf_ws());
+    const double* dinv2 = reinterpret_cast<const double*>(ws.potrf_ws2());
+    if (pe > 0) PB_TRY(trsv(st, M, pe, ldm, dinv1, false, rhs, z));
+    double* zhead = z;                   // z1 (later z1 - Y x2) lives here
+    if (m > 0) {
+        const unsigned nbm = vec_blocks(m);
+        if (pe > 0) {
+            PB_TRY(gemv(st, Yt, m, pe, ldm, z, tmp + pe));
+            sub_kernel<<<nbm, 256, 0, st>>>(rhs + pe, tmp + pe, m, tx + pe); pb::note_launch();
+        } else {
+            PB_CUDA(cudaMemcpyAsync(tx, rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        PB_TRY(trsv(st, Cb, m, ldm, dinv2, false, tx + pe, z + pe));
+        scale_kernel<<<nbm, 256, 0, st>>>(z + pe, -1.0, m, tx + pe); pb::note_launch();
+        PB_TRY(trsv(st, Cb, m, ldm, dinv2, true, tx + pe, rhs + pe));                      // x2
+        if (pe > 0) {
+            // z1 <- z1 - Y x2 = z1 - Yt^T x2, 1536 rows of Yt at a time (three partial slots), ping-pong z <-> tmp
+            double* part = ws.vec(V_P);                   // V_P, V_Q, V_Y are consecutive slots
+            double* cur = z;
+            double* nxt = tmp;
+            const unsigned nbp = vec_blocks(pe);
+            for (int64_t i0 = 0; i0 < m; i0 += 3 * 512) {
+                const int64_t rows = std::min<int64_t>(3 * 512, m - i0);
+                PB_TRY(gemv_t_partial(st, Yt + i0 * ldm, rows, pe, ldm, rhs + pe + i0, part, ws.L.vec_stride));
+                nystrom_z_kernel<<<nbp, 256, 0, st>>>(cur, part, gemv_t_splits(rows), ws.L.vec_stride, pe, nxt, ws.partial()); pb::note_launch();
+                std::swap(cur, nxt);
+            }
+            zhead = cur;
+        }
+    }
+    if (pe > 0) {
+        double* out = zhead == z ? tmp : z;               // trsv: x must not alias rhs
+        PB_TRY(trsv(st, M, pe, ldm, dinv1, true, zhead, out));
+        PB_CUDA(cudaMemcpyAsync(rhs, out, pe * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    scatter_perm_kernel<<<nb, 256, 0, st>>>(perm, np, rhs, ws.vec(V_C)); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
 
 // Residual target of a CG Newton solve.  The step is w+ = b - s o x with B x = c, so a residual r leaves
@@ -698,10 +880,6 @@ bool pcg_enabled(int64_t n) { return n >= opt_pcg_min_n(); }
 // of the factor-every-step iterates (eta = 1e-1: 1.6e-10; eta <= 1e-3: 1.7e-11, the FP64 floor).
 double cg_target(const pb_problem* prob, double tolerance) { return opt_cg_tol() * tolerance * prob->lik.sigma; }
 
-// Smallest curvature W = -h accepted as "zero" (pb_options.negative_curvature_tol, in units of 1/sigma^2).
-double curvature_floor(const pb_problem* prob) {
-    return -opts().negative_curvature_tol / (prob->lik.sigma * prob->lik.sigma);
-}
 
 }  // namespace
 
@@ -802,17 +980,31 @@ int pb::laplace_fit_impl(cudaStream_t st, const pb_problem* prob, double toleran
         if (it == 0) PB_CUDA(cudaMemsetAsync(ws.vec(V_F), 0, n * sizeof(double), st));   // K @ 0
         else PB_TRY(K_times(st, ws, n, w, ws.vec(V_F), nystrom_live && !have_factor ? ny.symv : nullptr));
         laplace_prep_kernel<<<nb, 256, 0, st>>>(lp, prob->lik.cutpoints, ws.vec(V_F), prob->y, n, curvature_floor(prob),
-                                                ws.vec(V_S), ws.vec(V_B), ws.partial()); pb::note_launch();
+                                                ws.vec(V_S), ws.vec(V_B), ws.vec(V_G), ws.partial()); pb::note_launch();
         PB_CUDA(cudaGetLastError());
         PB_TRY(finalize(st, ws, nb, ws.scalars() + S_SUMLL, ws.scalars() + S_BAD));
         PB_TRY(K_times(st, ws, n, ws.vec(V_B), ws.vec(V_T), nystrom_live && !have_factor ? ny.symv : nullptr));   // K b
         mul_kernel<<<nb, 256, 0, st>>>(ws.vec(V_S), ws.vec(V_T), n, ws.vec(V_C)); pb::note_launch();
+        // materially negative curvature somewhere?  (8-byte readback; the count decides the solver below)
+        PB_TRY(read_scalars(st, ws, host, nullptr));
+        const bool indefinite = host[S_BAD] > 0;
+        if (indefinite && sharded) {
+            set_error("laplace_fit (multi-GPU): %d data have negative likelihood curvature (< %.3g) at iteration %d; the "
+                      "signed-Cholesky Newton step is single-GPU only", (int)host[S_BAD], curvature_floor(prob), it + 1);
+            return PB_ERR_NUMERIC;
+        }
         // x = B^{-1} (s o K b).  Large n: CG with the Nystrom preconditioner, no factorisation at all.  If that
         // ever stalls, or below "laplace_pcg_min_n": the first iteration factors B; later ones reuse the last
         // factor as a PCG preconditioner (rescaled by s_fac/s) and refactor only if PCG stalls.
         const double* xsol = ws.vec(V_C);
         bool solved = false;
-        if (have_factor && prob->lik.kind == PB_LIK_GAUSSIAN) {
+        if (indefinite) {
+            PB_TRY(indefinite_newton_solve(st, prob, ws));      // x in V_C, V_S <- |W|^1/2
+            have_factor = false;                                 // the factor region now holds the signed factor
+            nystrom_warm = false;
+            result_host->factorizations += 1;
+            solved = true;
+        } else if (have_factor && prob->lik.kind == PB_LIK_GAUSSIAN) {
             // W = 1/sigma^2 does not depend on f: B is the matrix already factored, reuse it as is
             PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), false, ws.vec(V_C), ws.vec(V_X)));
             PB_TRY(trsv(st, ws.B(), n, ld, ws.dinv(), true, ws.vec(V_X), ws.vec(V_C)));
@@ -859,13 +1051,13 @@ int pb::laplace_fit_impl(cudaStream_t st, const pb_problem* prob, double toleran
         ++it;
         result_host->iterations = it;
         result_host->info = info_host;
-        if (host[S_BAD] > 0) {
-            set_error("laplace_fit: %d data have materially negative (< %.3g) or NaN likelihood curvature at iteration %d; "
-                      "the SPD Newton form needs W = -h >= 0", (int)host[S_BAD], curvature_floor(prob), it);
-            return PB_ERR_NUMERIC;
-        }
         if (info_host != 0) {
-            set_error("laplace_fit: Cholesky of I + W^1/2 K W^1/2 failed at column %d (iteration %d)", info_host, it);
+            if (indefinite)
+                set_error("laplace_fit: %d data have negative likelihood curvature at iteration %d and K^-1 + W is not positive "
+                          "definite there (signed Cholesky failed at column %d of the permuted matrix, or NaN curvature)",
+                          (int)host[S_BAD], it, info_host);
+            else
+                set_error("laplace_fit: Cholesky of I + W^1/2 K W^1/2 failed at column %d (iteration %d)", info_host, it);
             return PB_ERR_NUMERIC;
         }
         error = sqrt(host[S_ERR2]);

@@ -294,24 +294,30 @@ def test_nystrom_fit_ignores_stale_info_words():
     assert relerr(w1.cpu().numpy(), w0.cpu().numpy()) < 1e-13
 
 
-def test_small_noise_tail_curvature_is_clamped_not_fatal():
-    """with sigma = 0.1 data far in the tails have Z << 1e-10, where log(Z + 1e-10) has a
-    slightly POSITIVE second derivative (h ~ +1e-9).  The reference's LU Newton step just proceeds; the SPD form
-    treats such a datum as W = 0.  Same weights as the oracle's literal LU iteration."""
+@pytest.mark.parametrize("seed,N,D,J,family,sigma", [(17, 257, 1, 3, "eq", 0.08), (9, 500, 1, 5, "eq", 0.1),
+                                                          (4, 600, 3, 4, "eq", 0.18), (3, 350, 1, 3, "matern12", 0.1),
+                                                          (5, 400, 1, 3, "eq", 0.1)])
+def test_small_noise_negative_curvature_follows_the_reference_newton_iterates(seed, N, D, J, family, sigma):
+    """log(Z + 1e-10) is not log-concave where Z <~ 1e-10 — with a small noise std, data 5.5 .. 8.7
+    sigma outside their interval have h > 0 (up to ~9 / sigma^2).  The reference's LU Newton step (solvers.py:24) takes the
+    indefinite Jacobian as it comes.  The CUDA path must follow the same iterates: tiny negative curvature is clamped,
+    materially negative curvature goes through the signed Cholesky (fit.cu indefinite_newton_solve).  Same weights as the
+    oracle's literal LU iteration at the north-star tolerance, same iteration count.  (Where the reference itself fails
+    to converge — it wanders for maxiter = 100 iterations and returns precisions of -1e3 — there is nothing to match.)"""
     from probit_b200 import approximators as PA, kernels as PK, utilities as PU
-    X, y, params, family = ordinal_problem(17, 300, 2, 3, "eq")
-    cut = params[1][1]
-    sigma = 0.1
-    prm = (params[0], (sigma, cut))
+    X, y, params, family = ordinal_problem(seed, N, D, J, family)
+    prm = (params[0], (sigma, params[1][1]))
     o = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood)
     w_ref, p_ref = o.approximate_posterior(prm)
-    assert (p_ref < 0).any() or True                              # tails may or may not be reached at the optimum
+    assert len(o.trace) < 100                                     # cases where the reference's own Newton iteration converges
     gp = PA.LaplaceGP((X, y), make_prior(PK, family), PU.log_probit_likelihood)
-    w, prec = gp.approximate_posterior(prm)                       # must not raise at iteration 1 (f = 0: z = 10 for the top class)
-    assert relerr(w.cpu().numpy(), w_ref) < 1e-6
-    m, v = gp.predict(X[:20], prm, w, prec)
-    m_ref, v_ref = o.predict(X[:20], prm, w_ref, p_ref)
-    assert relerr(m.cpu().numpy(), m_ref) < 1e-6
+    w, prec = gp.approximate_posterior(prm)
+    assert gp.last_result.iterations == len(o.trace)
+    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+    if (p_ref > 0).all():                                         # predict needs K + P^-1 positive definite, as in the reference
+        m, v = gp.predict(X[:20], prm, w, prec)
+        m_ref, v_ref = o.predict(X[:20], prm, w_ref, p_ref)
+        assert relerr(m.cpu().numpy(), m_ref) < TOL and relerr(v.cpu().numpy(), v_ref) < TOL
 
 
 def test_configs2_regression_n16384_matches_closed_form():

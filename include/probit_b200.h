@@ -102,6 +102,10 @@ typedef struct pb_options {
                                      (N=16384: 64.8 vs 59.7 ms) — the look-ahead stream's priority does not survive
                                      capture, and eager issue is not host-bound */
     int32_t dist_block;           /* panel width of the multi-GPU block-cyclic factorisation, 0 = auto */
+    int32_t potrf_ozaki;          /* trailing updates of the Cholesky factorisation on the INT8 tensor cores (tcgen05
+                                     kind::i8 through error-free slicing, pb_ozaki_gemm_nt): -1 = auto (on for n >= 8192),
+                                     0 = FP64 DMMA only, 1 = wherever the shapes allow */
+    int32_t _reserved;
 } pb_options;
 int pb_options_default(pb_options* options);
 
@@ -170,6 +174,17 @@ int pb_transform_block(pb_stream_t stream, const double* K, int64_t ldk, const d
 int pb_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
                int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc,
                int32_t lower_only);
+
+/* The same contraction, C += alpha * A * B^T (no beta), on the INT8 tensor cores (tcgen05.mma.kind::i8, TMEM) by
+ * error-free slicing of the FP64 operands into 7 base-128 digit planes with one exponent per row (Ozaki scheme,
+ * csrc/ozaki.cu): 28 exact int8 x int8 -> int32 products per FP64 product, about 3x the FP64 DMMA rate.  K must be a
+ * multiple of 64.  lower_only != 0 is the SYRK form (A == B, M == N, only tiles on/below the diagonal are updated).
+ * The result differs from the FP64 product by ~2^-49 of (row scale of A) x (row scale of B) x sqrt(K).
+ * scratch: pb_ozaki_scratch_bytes(M, N, K), 256-byte aligned. */
+int64_t pb_ozaki_scratch_bytes(int64_t M, int64_t N, int64_t K);
+int pb_ozaki_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                     const double* B, int64_t ldb, double* C, int64_t ldc, int32_t lower_only, void* scratch,
+                     int64_t scratch_bytes);
 
 /* ---- K3/K8: level-2 kernels -------------------------------------------------------------------
  * pb_symv : y = K x for a full-storage symmetric K (Laplace.py:8,22; VB.py:9,23).

@@ -25,7 +25,7 @@ class Options(C.Structure):
     """pb_options: the tunables of the drivers, passed explicitly with every call (no global configuration)."""
     _fields_ = [("laplace_pcg_min_n", C.c_int64), ("laplace_nystrom_rank", C.c_int64), ("laplace_cg_tol", C.c_double),
                 ("negative_curvature_tol", C.c_double), ("potrf_block", C.c_int32), ("potrf_lookahead", C.c_int32),
-                ("potrf_graph", C.c_int32), ("dist_block", C.c_int32)]
+                ("potrf_graph", C.c_int32), ("dist_block", C.c_int32), ("potrf_ozaki", C.c_int32), ("_reserved", C.c_int32)]
 
 
 class LikelihoodSpec(C.Structure):
@@ -79,6 +79,8 @@ SIGNATURES = {
     "pb_rebuild_solve_workspace": (_i32, [_p, _p, _i64, _i64, _p, _i64]),
     "pb_transform_block": (_i32, [_p, _p, _i64, _p, _f64, _f64, _i64, _i64, _i64, _i64, _p, _i64]),
     "pb_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _f64, _p, _i64, _i32]),
+    "pb_ozaki_scratch_bytes": (_i64, [_i64, _i64, _i64]),
+    "pb_ozaki_gemm_nt": (_i32, [_p, _i64, _i64, _i64, _f64, _p, _i64, _p, _i64, _p, _i64, _i32, _p, _i64]),
     "pb_symv": (_i32, [_p, _p, _i64, _i64, _p, _p]),
     "pb_symv_lower_scratch_bytes": (_i64, [_i64]),
     "pb_gemv": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p]),

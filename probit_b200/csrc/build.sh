@@ -7,7 +7,7 @@ OUT=../libprobit_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr -Wno-deprecated-gpu-targets"
 OBJ=../../build/obj
 mkdir -p $OBJ
-SRCS="capi gemm_dmma potrf likelihood gram blas2 fit dist"
+SRCS="capi gemm_dmma ozaki potrf likelihood gram blas2 fit dist"
 pids=""
 for f in $SRCS; do
   ( $NVCC $FLAGS -c $f.cu -o $OBJ/$f.o 2> $OBJ/$f.ptxas.log || { cat $OBJ/$f.ptxas.log; exit 1; } ) &

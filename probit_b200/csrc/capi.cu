@@ -45,6 +45,8 @@ static pb_options default_options() {
     o.potrf_lookahead = 1;
     o.potrf_graph = 0;                 // measured slower than eager issue on B200: opt-in
     o.dist_block = 0;
+    o.potrf_ozaki = 0;
+    o._reserved = 0;
     return o;
 }
 static const pb_options g_defaults = default_options();

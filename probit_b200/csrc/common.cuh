@@ -153,6 +153,17 @@ int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, 
 int gemm_nt_mode(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                  const double* B, int64_t ldb, double beta, double* C, int64_t ldc, int lower_only);
 
+int gemm_nt_groups(cudaStream_t stream, const double* P, int64_t ldp, int64_t R, int64_t K, double alpha, double beta,
+                   double* c0, int64_t ldc, int64_t cstep, int count, int64_t a0, int64_t astep, int64_t nb);
+
+// ozaki.cu: FP64 contractions on the INT8 tensor cores (tcgen05 kind::i8) by error-free slicing
+bool ozaki_supported(int64_t K);
+int64_t ozaki_scratch_bytes(int64_t rows, int64_t K);
+int ozaki_syrk_lower(cudaStream_t st, int64_t n, int64_t K, double alpha, const double* P, int64_t ldp, double* C,
+                     int64_t ldc, void* scratch, int64_t scratch_bytes);
+int ozaki_gemm_nt(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                  const double* B, int64_t ldb, double* C, int64_t ldc, void* scratch, int64_t scratch_bytes);
+
 // potrf.cu
 int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
           int32_t* info);

@@ -171,12 +171,53 @@ Bc make_bc(const Ws& ws) {
 // k0.. of the factor's columns [k0, k0 + w) in `P`, leading dimension nb) is on this rank.
 using PanelHook = std::function<int(int64_t, int64_t, int64_t, const double*, const double*)>;
 
-enum { EV_RECV = 0, EV_PACKED, EV_TRAIL, EV_COLREADY, EV_KINDS };
+enum { EV_RECV = 0, EV_PACKED, EV_TRAIL, EV_COLREADY, EV_COPIED, EV_KINDS };
 
 struct Events {
     Comm* c;
     int get(int kind, int64_t k, cudaEvent_t* e) const { return comm_event(c, (size_t)(k * EV_KINDS + kind) + 1, e); }
 };
+
+// Optional timeline of one factorisation (debugging aid): PB_DIST_TRACE=<path prefix> makes every rank write
+// <prefix>.<rank>.csv with, per panel step, the start / end times (ms from the first event) of the trailing update on
+// the main stream, of the look-ahead panel work on the side stream and of the panel broadcast on the communication
+// stream.  Costs a device synchronise at the end of the factorisation; off by default.
+struct Trace {
+    struct Rec { int kind; int64_t k; cudaEvent_t e; };
+    std::vector<Rec> recs;
+    const char* prefix = nullptr;
+    Trace() { const char* p = getenv("PB_DIST_TRACE"); if (p && *p) prefix = p; }
+    bool on() const { return prefix != nullptr; }
+    void mark(int kind, int64_t k, cudaStream_t s) {
+        if (!on()) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, s);
+        recs.push_back({kind, k, e});
+    }
+    void dump(int rank, int64_t nblk) {
+        if (!on() || recs.empty()) return;
+        cudaDeviceSynchronize();
+        char path[512];
+        snprintf(path, sizeof(path), "%s.%d.csv", prefix, rank);
+        FILE* f = fopen(path, "w");
+        if (f) {
+            std::vector<float> t(6 * nblk, -1.f);
+            for (const Rec& r : recs) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, recs[0].e, r.e) == cudaSuccess && r.k >= 0 && r.k < nblk) t[r.k * 6 + r.kind] = ms;
+            }
+            fprintf(f, "k,main_start,main_end,side_start,side_end,bcast_start,bcast_end\n");
+            for (int64_t k = 0; k < nblk; ++k)
+                fprintf(f, "%lld,%.3f,%.3f,%.3f,%.3f,%.3f,%.3f\n", (long long)k, t[k * 6], t[k * 6 + 1], t[k * 6 + 2], t[k * 6 + 3],
+                        t[k * 6 + 4], t[k * 6 + 5]);
+            fclose(f);
+        }
+        for (const Rec& r : recs) cudaEventDestroy(r.e);
+        recs.clear();
+    }
+};
+enum { TR_MAIN0 = 0, TR_MAIN1, TR_SIDE0, TR_SIDE1, TR_BC0, TR_BC1 };
 
 // Owner: copy factored block column k (rows k0.., strided) + its leaf inverses into the contiguous panel message.
 int pack_panel(cudaStream_t s, const Ws& ws, const Bc& b, int64_t k, const double* leaf_inv) {
@@ -196,29 +237,62 @@ int update_column(cudaStream_t s, const Ws& ws, const Bc& b, int64_t j, int64_t 
                    b.ld_loc, false);
 }
 
-// Factor block column k in place on stream s (diagonal block + the rows below), keep its leaf inverses, pack it.
-int factor_column(cudaStream_t s, const Ws& ws, const Bc& b, int64_t k, int32_t* info_panel) {
+// Factor block column k on stream s (diagonal block + the rows below), keep its leaf inverses, and leave the packed
+// panel message in ws.panel(k).
+// Fast path (w a multiple of 256): the rows below the diagonal block are solved with the 256 x 256 diagonal-block
+// inverses potrf leaves in its workspace — X_b <- (X_b - sum_{a<b} Y_a L_ba^T) L_bb^-T, one or two large GEMMs per
+// 256 columns instead of the 15 dependent launches of the recursive TRSM — and the results go STRAIGHT into the
+// message (out of place), so the 2-D pack copy of the whole column disappears from the panel's critical path.  The
+// local copy of the factor (needed by bc_stream later) is refreshed from the message afterwards (*copy_back).
+int factor_column(cudaStream_t s, const Ws& ws, const Bc& b, int64_t k, int32_t* info_panel, bool* copy_back) {
     const int64_t w = b.width(k), k0 = k * b.nb, below = b.n - k0 - w;
     double* A = b.col(k);
+    *copy_back = false;
     PB_TRY(potrf(s, A, w, b.ld_loc, ws.potrf_ws(), pb_potrf_workspace_bytes(b.nb), info_panel));
     fold_info_kernel<<<1, 1, 0, s>>>(info_panel, (int32_t)k0, ws.info()); pb::note_launch();
-    if (below > 0) PB_TRY(trsm_right_lt(s, A, w, b.ld_loc, ws.potrf_ws(), A + w * b.ld_loc, below, b.ld_loc));
     double* keep = ws.dinv_store() + (k / b.world) * b.nb * 64;
     PB_CUDA(cudaMemsetAsync(keep, 0, b.nb * 64 * sizeof(double), s));
     PB_CUDA(cudaMemcpyAsync(keep, ws.dinv(), ceil_div<int64_t>(w, 64) * 64 * 64 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    if (below > 0 && w % 256 == 0 && w == b.nb) {
+        double* msg = ws.panel(k);
+        double* Y = msg + b.nb * 64 + w * b.nb;                      // rows below the diagonal block inside the message
+        double* X = A + w * b.ld_loc;
+        const double* tinv = ws.dinv() + ceil_div<int64_t>(w, 64) * 64 * 64;    // L_bb^-1, row-major, 256 x 256 each
+        for (int64_t c = 0; c < w; c += 256) {
+            if (c > 0) PB_TRY(gemm_nt(s, below, 256, c, -1.0, Y, b.nb, A + c * b.ld_loc, b.ld_loc, 1.0, X + c, b.ld_loc, false));
+            PB_TRY(gemm_nt(s, below, 256, 256, 1.0, X + c, b.ld_loc, tinv + (c / 256) * 256 * 256, 256, 0.0, Y + c, b.nb, false));
+        }
+        PB_CUDA(cudaMemcpyAsync(msg, keep, b.nb * 64 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        PB_CUDA(cudaMemcpy2DAsync(msg + b.nb * 64, b.nb * sizeof(double), A, b.ld_loc * sizeof(double), w * sizeof(double), w,
+                                  cudaMemcpyDeviceToDevice, s));
+        *copy_back = true;
+        return PB_OK;
+    }
+    if (below > 0) PB_TRY(trsm_right_lt(s, A, w, b.ld_loc, ws.potrf_ws(), A + w * b.ld_loc, below, b.ld_loc));
     return pack_panel(s, ws, b, k, keep);
+}
+
+// Owner, after the panel is on its way: refresh the local block column below the diagonal from the message.
+int unpack_column(cudaStream_t s, const Ws& ws, const Bc& b, int64_t k) {
+    const int64_t w = b.width(k), below = b.n - k * b.nb - w;
+    if (below <= 0) return PB_OK;
+    PB_CUDA(cudaMemcpy2DAsync(b.col(k) + w * b.ld_loc, b.ld_loc * sizeof(double), ws.panel(k) + b.nb * 64 + w * b.nb,
+                              b.nb * sizeof(double), w * sizeof(double), below, cudaMemcpyDeviceToDevice, s));
+    return PB_OK;
 }
 
 // Enqueue the broadcast of panel k (root = its owner) on the communication stream and record EV_RECV[k].
 // `free_after` (may be null) is the event after which this rank's target buffer is no longer read.
-int ship_panel(Comm* c, const Ws& ws, const Bc& b, const Events& ev, int64_t k, cudaEvent_t free_after) {
+int ship_panel(Comm* c, const Ws& ws, const Bc& b, const Events& ev, int64_t k, cudaEvent_t free_after, Trace* tr = nullptr) {
     cudaEvent_t packed, recv;
     PB_TRY(ev.get(EV_PACKED, k, &packed));
     PB_TRY(ev.get(EV_RECV, k, &recv));
     cudaStream_t cs = c->comm_stream;
     if (free_after) PB_CUDA(cudaStreamWaitEvent(cs, free_after, 0));
     if (b.owner(k) == b.me) PB_CUDA(cudaStreamWaitEvent(cs, packed, 0));
+    if (tr) tr->mark(TR_BC0, k, cs);
     PB_TRY(comm_broadcast(c, cs, ws.panel(k), b.count(k), b.owner(k)));
+    if (tr) tr->mark(TR_BC1, k, cs);
     PB_CUDA(cudaEventRecord(recv, cs));
     return PB_OK;
 }
@@ -232,6 +306,9 @@ int bc_factor(Comm* c, cudaStream_t st, const Ws& ws, const pb_problem* prob, co
     const int Df = feature_dim(prob->kernel, prob->D);
     cudaStream_t side = c->side_stream;
     int32_t* info_panel = ws.info() + 2;
+    Trace trace;
+    Trace* tr = trace.on() ? &trace : nullptr;
+    if (tr) tr->mark(TR_MAIN0, -1, st);
     PB_CUDA(cudaMemsetAsync(ws.info(), 0, 256, st));
     // every rank fills the block columns it owns (rows j0.. only): 8 N^2 / (2G) bytes, no communication
     for (int64_t j = b.me; j < b.nblk; j += b.world)
@@ -245,10 +322,17 @@ int bc_factor(Comm* c, cudaStream_t st, const Ws& ws, const pb_problem* prob, co
     if (b.owner(0) == b.me) {
         cudaEvent_t packed;
         PB_TRY(ev.get(EV_PACKED, 0, &packed));
-        PB_TRY(factor_column(side, ws, b, 0, info_panel));
+        if (tr) tr->mark(TR_SIDE0, 0, side);
+        bool copy_back = false;
+        PB_TRY(factor_column(side, ws, b, 0, info_panel, &copy_back));
+        if (tr) tr->mark(TR_SIDE1, 0, side);
         PB_CUDA(cudaEventRecord(packed, side));
+        cudaEvent_t copied;
+        PB_TRY(ev.get(EV_COPIED, 0, &copied));
+        if (copy_back) PB_TRY(unpack_column(side, ws, b, 0));
+        PB_CUDA(cudaEventRecord(copied, side));
     }
-    PB_TRY(ship_panel(c, ws, b, ev, 0, nullptr));
+    PB_TRY(ship_panel(c, ws, b, ev, 0, nullptr, tr));
     for (int64_t k = 0; k < b.nblk; ++k) {
         cudaEvent_t recv_k, trail_k, trail_km2 = nullptr;
         PB_TRY(ev.get(EV_RECV, k, &recv_k));
@@ -266,29 +350,55 @@ int bc_factor(Comm* c, cudaStream_t st, const Ws& ws, const pb_problem* prob, co
                     PB_CUDA(cudaStreamWaitEvent(side, ready, 0));
                 }
                 if (trail_km2) PB_CUDA(cudaStreamWaitEvent(side, trail_km2, 0));
+                if (tr) tr->mark(TR_SIDE0, nx, side);
                 PB_TRY(update_column(side, ws, b, nx, k));
-                PB_TRY(factor_column(side, ws, b, nx, info_panel));
+                bool copy_back = false;
+                PB_TRY(factor_column(side, ws, b, nx, info_panel, &copy_back));
+                if (tr) tr->mark(TR_SIDE1, nx, side);
                 PB_TRY(ev.get(EV_PACKED, nx, &packed));
                 PB_CUDA(cudaEventRecord(packed, side));
+                cudaEvent_t copied;
+                PB_TRY(ev.get(EV_COPIED, nx, &copied));
+                if (copy_back) PB_TRY(unpack_column(side, ws, b, nx));     // off the critical path: the broadcast is already released
+                PB_CUDA(cudaEventRecord(copied, side));
             }
-            PB_TRY(ship_panel(c, ws, b, ev, nx, trail_km2));
+            PB_TRY(ship_panel(c, ws, b, ev, nx, trail_km2, tr));
         }
         PB_CUDA(cudaStreamWaitEvent(st, recv_k, 0));
+        if (tr) tr->mark(TR_MAIN0, k, st);
         // trailing update of the owned block columns right of the look-ahead column, nearest first: column k+2 is
         // the next one the panel chain needs, so it is released (EV_COLREADY) before the rest of the update
         int64_t first = k + 2;
         first += ((b.me - first) % b.world + b.world) % b.world;            // first owned column >= k + 2
-        for (int64_t j = first; j < b.nblk; j += b.world) {
+        int64_t j = first;
+        if (j < b.nblk && j == k + 2) {
             PB_TRY(update_column(st, ws, b, j, k));
-            if (j == k + 2) {
-                cudaEvent_t ready;
-                PB_TRY(ev.get(EV_COLREADY, j, &ready));
-                PB_CUDA(cudaEventRecord(ready, st));
+            cudaEvent_t ready;
+            PB_TRY(ev.get(EV_COLREADY, j, &ready));
+            PB_CUDA(cudaEventRecord(ready, st));
+            j += b.world;
+        }
+        if (j < b.nblk) {
+            const int64_t count = (b.nblk - 1 - j) / b.world + 1;
+            if (count >= 2 && b.nb % 128 == 0 && b.width(k) == b.nb) {
+                // every remaining owned block column in ONE grid (gemm_dmma.cu GemmGroups): group q is column j + q world
+                PB_TRY(gemm_nt_groups(st, ws.panel(k) + b.nb * 64, b.nb, b.n - k * b.nb, b.nb, -1.0, 1.0, b.col(j), b.ld_loc,
+                                      (int64_t)b.world * b.nb * b.ld_loc + b.nb, (int)count, (j - k) * b.nb,
+                                      (int64_t)b.world * b.nb, b.nb));
+            } else {
+                for (; j < b.nblk; j += b.world) PB_TRY(update_column(st, ws, b, j, k));
             }
         }
         if (hook) PB_TRY(hook(k, k * b.nb, b.width(k), ws.panel(k), ws.panel(k) + b.nb * 64));
+        if (b.owner(k) == b.me) {            // the local copy of column k is refreshed from buffer k % 3: keep the buffer until then
+            cudaEvent_t copied;
+            PB_TRY(ev.get(EV_COPIED, k, &copied));
+            PB_CUDA(cudaStreamWaitEvent(st, copied, 0));
+        }
+        if (tr) tr->mark(TR_MAIN1, k, st);
         PB_CUDA(cudaEventRecord(trail_k, st));
     }
+    if (tr) tr->dump(b.me, b.nblk);
     // smallest failing column over the ranks -> ws.info() on every rank
     info_encode_kernel<<<1, 1, 0, st>>>(ws.info(), c->dev_i64); pb::note_launch();
     PB_TRY(comm_allreduce_max_i64(c, st, c->dev_i64, 1));

@@ -696,18 +696,19 @@ double curvature_floor(const pb_problem* prob) {
     return -opts().negative_curvature_tol / (prob->lik.sigma * prob->lik.sigma);
 }
 
-// ---- Newton step with indefinite curvature: signed Cholesky ----
+// ---- Newton step with indefinite curvature: block elimination ----
 // With W = S D S, S = |W|^1/2, D = diag(+-1):   (I + W K)^-1 = I - S (D + S K S)^-1 S K   (for D = I this is the B form).
 // M = D + S K S is symmetric indefinite.  Order the data with non-negative curvature first (p of them, stable) and
 // those with negative curvature last (m):
-//     M = [ B+   E^T ]      B+ = I + S+ K++ S+  (SPD),     M = L diag(I_p, -I_m) L^T,   L = [ L+    0  ]
-//         [ E    C0  ]      C0 = -I + S- K-- S-                                              [ Y^T  Lc ]
-// with L+ L+^T = B+, Y^T = E L+^-T and Lc Lc^T = Y^T Y - C0 = I - S- Sigma-- S-, Sigma = (K^-1 + W+)^-1.  The last
-// matrix is SPD exactly when the full Hessian K^-1 + W is positive definite, i.e. when the Newton step the reference
-// takes with its LU solve (solvers.py:24) is a step towards a minimum; otherwise the second potrf reports it.  Every
-// piece is an existing kernel (potrf, right-TRSM, SYRK, trsv, gemv) on a permuted matrix generated from permuted
-// features; p is made even with a decoupled dummy row so that the second block stays 16-byte aligned for TMA.
-// Cost: one N^3/3 factorisation for that Newton step — the rare path (small sigma or far-out cutpoints).
+//     M = [ B+   E^T ]      B+ = I + S+ K++ S+  (always SPD: Cholesky, right-TRSM and GEMM on the tensor cores),
+//         [ E    C0  ]      C0 = -I + S- K-- S-
+//     Yt = E L+^-T,   C = C0 - Yt Yt^T  (m x m Schur complement, symmetric, in general INDEFINITE),
+//     z1 = L+^-1 c1,  C x2 = c2 - Yt z1  (Gaussian elimination with partial pivoting),  x1 = L+^-T (z1 - Yt^T x2).
+// This is the solution the reference's LU solve (solvers.py:24) returns whenever I + W K is non-singular, whatever
+// the inertia of the Hessian — the reference walks through non-convex regions of log(Z + 1e-10) and still converges.
+// The permuted matrix is generated from permuted features; p is made even with a decoupled dummy row so that the
+// second block column stays 16-byte aligned for TMA.  Cost: one p^3/3 factorisation + m^3/3 elimination traffic for
+// that Newton step — the rare path (small sigma or far-out cutpoints); m is the number of offending data.
 __global__ void __launch_bounds__(1024)
 partition_kernel(const double* __restrict__ W, int64_t n, double neg_floor, long long* __restrict__ perm,
                  long long* __restrict__ counts) {
@@ -771,24 +772,80 @@ diag_add_kernel(double* __restrict__ A, int64_t ld, int64_t i0, int64_t i1, doub
     for (int64_t i = i0 + blockIdx.x * 256ll + threadIdx.x; i < i1; i += (int64_t)gridDim.x * 256) A[i * ld + i] += delta;
 }
 
-// lower triangle of the m x m block: A <- -A
-__global__ void __launch_bounds__(256)
-negate_lower_kernel(double* __restrict__ A, int64_t ld, int64_t m) {
-    const int64_t r = blockIdx.x;
-    for (int64_t c = threadIdx.x; c <= r; c += 256) A[r * ld + c] = -A[r * ld + c];
+// Gaussian elimination with partial pivoting on [C | rhs] (C m x m row-major, full storage), one column per pair of
+// launches: (1) pivot search in column k + row swap, (2) elimination of the rows below.  Singular pivot -> *info.
+__global__ void __launch_bounds__(1024)
+lu_pivot_kernel(double* __restrict__ C, int64_t ld, int m, int k, double* __restrict__ rhs, int32_t* __restrict__ info,
+                int32_t info_value) {
+    __shared__ double bestv[32];
+    __shared__ int besti[32];
+    __shared__ int piv;
+    double v = -1.0;
+    int idx = k;
+    for (int i = k + threadIdx.x; i < m; i += 1024) {
+        const double a = fabs(C[(int64_t)i * ld + k]);
+        if (a > v) { v = a; idx = i; }                          // NaN never wins: a NaN column ends with pivot 0 or NaN below
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bestv[threadIdx.x >> 5] = v; besti[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        v = bestv[threadIdx.x];
+        idx = besti[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+            if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+        }
+        if (threadIdx.x == 0) {
+            piv = idx;
+            if (!(v > 0.0)) atomicCAS(info, 0, info_value);
+        }
+    }
+    __syncthreads();
+    const int p = piv;
+    if (p != k) {
+        for (int j = k + threadIdx.x; j < m; j += 1024) {
+            const double a = C[(int64_t)k * ld + j], b = C[(int64_t)p * ld + j];
+            C[(int64_t)k * ld + j] = b;
+            C[(int64_t)p * ld + j] = a;
+        }
+        if (threadIdx.x == 0) { const double a = rhs[k]; rhs[k] = rhs[p]; rhs[p] = a; }
+    }
 }
 
 __global__ void __launch_bounds__(256)
-scale_kernel(const double* __restrict__ a, double alpha, int64_t n, double* __restrict__ out) {
-    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) out[i] = alpha * a[i];
+lu_eliminate_kernel(double* __restrict__ C, int64_t ld, int m, int k, double* __restrict__ rhs) {
+    const int i = k + 1 + blockIdx.x;
+    const double f = C[(int64_t)i * ld + k] / C[(int64_t)k * ld + k];
+    const double* pr = C + (int64_t)k * ld;
+    double* row = C + (int64_t)i * ld;
+    for (int j = k + 1 + threadIdx.x; j < m; j += 256) row[j] = fma(-f, pr[j], row[j]);
+    if (threadIdx.x == 0) rhs[i] = fma(-f, rhs[k], rhs[i]);
 }
 
-__global__ void fold_info2_kernel(int32_t* __restrict__ info, const int32_t* __restrict__ info2, int32_t offset) {
-    if (*info == 0 && *info2 != 0) *info = *info2 + offset;
+// back substitution with the upper factor left in C: rhs <- U^-1 rhs (one CTA)
+__global__ void __launch_bounds__(1024)
+lu_backsub_kernel(const double* __restrict__ C, int64_t ld, int m, double* __restrict__ rhs) {
+    __shared__ double xk;
+    for (int k = m - 1; k >= 0; --k) {
+        if (threadIdx.x == 0) {
+            xk = rhs[k] / C[(int64_t)k * ld + k];
+            rhs[k] = xk;
+        }
+        __syncthreads();
+        const double x = xk;
+        for (int i = threadIdx.x; i < k; i += 1024) rhs[i] = fma(-C[(int64_t)i * ld + k], x, rhs[i]);
+        __syncthreads();
+    }
 }
 
 // x (V_C, original order) = (D + S K S)^-1 (S o t), t = K b in V_T, signed W in V_G; V_S <- |W|^1/2.
-// Overwrites the factor region, both potrf workspaces and the PCG vector slots.
+// Overwrites the factor region, the potrf workspace and the PCG vector slots.
 int indefinite_newton_solve(cudaStream_t st, const pb_problem* prob, const Ws& ws) {
     const int64_t n = prob->n;
     const int Df = feature_dim(prob->kernel, prob->D);
@@ -815,39 +872,34 @@ int indefinite_newton_solve(cudaStream_t st, const pb_problem* prob, const Ws& w
     }
     const int64_t pws_bytes = pb_potrf_workspace_bytes(n + 1);
     double* Yt = M + pe * ldm;            // m x pe
-    double* Cb = Yt + pe;                 // m x m
-    int32_t* info2 = ws.info() + 3;
+    double* Cb = Yt + pe;                 // m x m (full storage: the Schur complement is eliminated with row pivoting)
     if (pe > 0) PB_TRY(potrf(st, M, pe, ldm, ws.potrf_ws(), pws_bytes, ws.info()));
     else PB_CUDA(cudaMemsetAsync(ws.info(), 0, sizeof(int32_t), st));
-    if (m > 0) {
-        if (pe > 0) {
-            PB_TRY(trsm_right_lt(st, M, pe, ldm, ws.potrf_ws(), Yt, m, ldm));
-            PB_TRY(gemm_nt(st, m, m, pe, 1.0, Yt, ldm, Yt, ldm, -1.0, Cb, ldm, true));          // Y^T Y - C0
-        } else {
-            negate_lower_kernel<<<(unsigned)m, 256, 0, st>>>(Cb, ldm, m); pb::note_launch();
-            PB_CUDA(cudaGetLastError());
-        }
-        PB_TRY(potrf(st, Cb, m, ldm, ws.potrf_ws2(), pws_bytes, info2));
-        fold_info2_kernel<<<1, 1, 0, st>>>(ws.info(), info2, (int32_t)pe); pb::note_launch();
+    if (m > 0 && pe > 0) {
+        PB_TRY(trsm_right_lt(st, M, pe, ldm, ws.potrf_ws(), Yt, m, ldm));
+        PB_TRY(gemm_nt(st, m, m, pe, -1.0, Yt, ldm, Yt, ldm, 1.0, Cb, ldm, false));              // C = C0 - Yt Yt^T
     }
-    // L z = c ; z2 <- -z2 ; L^T x = z
     const double* dinv1 = reinterpret_cast<const double*>(ws.potrf_ws());
-    const double* dinv2 = reinterpret_cast<const double*>(ws.potrf_ws2());
-    if (pe > 0) PB_TRY(trsv(st, M, pe, ldm, dinv1, false, rhs, z));
-    double* zhead = z;                   // z1 (later z1 - Y x2) lives here
+    if (pe > 0) PB_TRY(trsv(st, M, pe, ldm, dinv1, false, rhs, z));                              // z1 = L+^-1 c1
+    double* zhead = z;                   // z1 (later z1 - Yt^T x2) lives here
     if (m > 0) {
         const unsigned nbm = vec_blocks(m);
+        double* c2 = tx + pe;            // right-hand side of the Schur system, overwritten by x2
         if (pe > 0) {
             PB_TRY(gemv(st, Yt, m, pe, ldm, z, tmp + pe));
-            sub_kernel<<<nbm, 256, 0, st>>>(rhs + pe, tmp + pe, m, tx + pe); pb::note_launch();
+            sub_kernel<<<nbm, 256, 0, st>>>(rhs + pe, tmp + pe, m, c2); pb::note_launch();
         } else {
-            PB_CUDA(cudaMemcpyAsync(tx, rhs, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            PB_CUDA(cudaMemcpyAsync(c2, rhs + pe, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
         }
-        PB_TRY(trsv(st, Cb, m, ldm, dinv2, false, tx + pe, z + pe));
-        scale_kernel<<<nbm, 256, 0, st>>>(z + pe, -1.0, m, tx + pe); pb::note_launch();
-        PB_TRY(trsv(st, Cb, m, ldm, dinv2, true, tx + pe, rhs + pe));                      // x2
+        for (int64_t k = 0; k < m; ++k) {
+            lu_pivot_kernel<<<1, 1024, 0, st>>>(Cb, ldm, (int)m, (int)k, c2, ws.info(), (int32_t)(pe + k + 1)); pb::note_launch();
+            if (k + 1 < m) { lu_eliminate_kernel<<<(unsigned)(m - k - 1), 256, 0, st>>>(Cb, ldm, (int)m, (int)k, c2); pb::note_launch(); }
+        }
+        lu_backsub_kernel<<<1, 1024, 0, st>>>(Cb, ldm, (int)m, c2); pb::note_launch();          // x2
+        PB_CUDA(cudaGetLastError());
+        PB_CUDA(cudaMemcpyAsync(rhs + pe, c2, m * sizeof(double), cudaMemcpyDeviceToDevice, st));
         if (pe > 0) {
-            // z1 <- z1 - Y x2 = z1 - Yt^T x2, 1536 rows of Yt at a time (three partial slots), ping-pong z <-> tmp
+            // z1 <- z1 - Yt^T x2, 1536 rows of Yt at a time (three partial slots), ping-pong z <-> tmp
             double* part = ws.vec(V_P);                   // V_P, V_Q, V_Y are consecutive slots
             double* cur = z;
             double* nxt = tmp;
@@ -863,7 +915,7 @@ int indefinite_newton_solve(cudaStream_t st, const pb_problem* prob, const Ws& w
     }
     if (pe > 0) {
         double* out = zhead == z ? tmp : z;               // trsv: x must not alias rhs
-        PB_TRY(trsv(st, M, pe, ldm, dinv1, true, zhead, out));
+        PB_TRY(trsv(st, M, pe, ldm, dinv1, true, zhead, out));                                   // x1 = L+^-T (z1 - Yt^T x2)
         PB_CUDA(cudaMemcpyAsync(rhs, out, pe * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     scatter_perm_kernel<<<nb, 256, 0, st>>>(perm, np, rhs, ws.vec(V_C)); pb::note_launch();
@@ -1000,7 +1052,7 @@ int pb::laplace_fit_impl(cudaStream_t st, const pb_problem* prob, double toleran
         bool solved = false;
         if (indefinite) {
             PB_TRY(indefinite_newton_solve(st, prob, ws));      // x in V_C, V_S <- |W|^1/2
-            have_factor = false;                                 // the factor region now holds the signed factor
+            have_factor = false;                                 // the factor region now holds the block-eliminated matrix
             nystrom_warm = false;
             result_host->factorizations += 1;
             solved = true;
@@ -1053,8 +1105,8 @@ int pb::laplace_fit_impl(cudaStream_t st, const pb_problem* prob, double toleran
         result_host->info = info_host;
         if (info_host != 0) {
             if (indefinite)
-                set_error("laplace_fit: %d data have negative likelihood curvature at iteration %d and K^-1 + W is not positive "
-                          "definite there (signed Cholesky failed at column %d of the permuted matrix, or NaN curvature)",
+                set_error("laplace_fit: %d data have negative likelihood curvature at iteration %d and the Newton matrix I + W K is "
+                          "singular (or NaN) there: elimination broke down at column %d of the permuted matrix",
                           (int)host[S_BAD], it, info_host);
             else
                 set_error("laplace_fit: Cholesky of I + W^1/2 K W^1/2 failed at column %d (iteration %d)", info_host, it);

@@ -18,6 +18,7 @@
 //  * `lower_only` enumerates only tiles with tile_n <= tile_m in L2-friendly column strips.
 #include "common.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace pb {
 
@@ -144,11 +145,24 @@ __device__ __forceinline__ void lower_tile_2to1(int bid, int& tm, int& tn) {
     tn = bid - r * (r + 1);
 }
 
+// lower_only == 3: "grouped" mode for the block-column-cyclic trailing update of the multi-GPU Cholesky (dist.cu).
+// A and B are the SAME panel (R rows); group q updates one owned block column:
+//     C_q[M_q x N_q] += alpha * P[a0 + q astep :, :] * P[a0 + q astep : +N_q, :]^T,   M_q = R - (a0 + q astep), N_q = min(nb, M_q),
+// C_q = c0 + q cstep (leading dimension ldc).  One launch covers every group, so a panel step is one grid of
+// thousands of tiles instead of a launch per block column (each with its own ramp and tail).
+struct GemmGroups {
+    int count = 0;          // groups
+    int R = 0;              // rows of the panel
+    int a0 = 0, astep = 0;  // panel row of group 0 / increment per group
+    int nb = 0;             // block column width
+    int64_t cstep = 0;      // elements between the C origins of consecutive groups
+};
+
 template <class CF>
 __global__ void __launch_bounds__(CF::THREADS, CF::MIN_CTAS)
 gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, double beta,
-               int lower_only, int tiles_n) {
+               double* __restrict__ C_arg, int64_t ldc, int M_arg, int N_arg, int K, double alpha, double beta,
+               int lower_only, int tiles_n, const GemmGroups grp) {
     constexpr int BM = CF::BM, BN = CF::BN, STAGES = CF::STAGES, CONSUMER_WARPS = CF::CONSUMER_WARPS;
     constexpr int A_STAGE_BYTES = CF::A_STAGE_BYTES, STAGE_BYTES = CF::STAGE_BYTES;
     constexpr int MI = CF::MI, NJ = CF::NJ, WARP_M = CF::WARP_M, WARP_N = CF::WARP_N;
@@ -157,7 +171,24 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t bar_base = smem_base + STAGES * STAGE_BYTES;   // full[s] at +8s, empty[s] at +8(STAGES+s)
 
     int tile_m, tile_n;
-    if (lower_only) {
+    int M = M_arg, N = N_arg, a_row0 = 0;         // a_row0: panel row of this tile's group (grouped mode)
+    double* C = C_arg;
+    if (lower_only == 3) {
+        int b = (int)blockIdx.x, q = 0;
+        for (;; ++q) {
+            const int Mq = grp.R - (grp.a0 + q * grp.astep);
+            const int t = ((Mq + BM - 1) / BM) * tiles_n;
+            if (b < t || q + 1 >= grp.count) break;
+            b -= t;
+        }
+        a_row0 = grp.a0 + q * grp.astep;
+        M = grp.R - a_row0;
+        N = M < grp.nb ? M : grp.nb;
+        C = C_arg + (int64_t)q * grp.cstep;
+        tile_m = b / tiles_n;
+        tile_n = b % tiles_n;
+        lower_only = 0;
+    } else if (lower_only) {
         if (CF::BM == CF::BN) lower_tile(blockIdx.x, tiles_n, tile_m, tile_n);
         else lower_tile_2to1(blockIdx.x, tile_m, tile_n);
     } else {
@@ -190,8 +221,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const uint32_t full = bar_base + 8 * s;
         mbar_expect_tx(full, STAGE_BYTES);
         const uint32_t dstA = smem_base + s * STAGE_BYTES;
-        tma_load_2d(dstA, &mapA, k_begin + kb * BK, m0, full);
-        tma_load_2d(dstA + A_STAGE_BYTES, &mapB, k_begin + kb * BK, n0, full);
+        tma_load_2d(dstA, &mapA, k_begin + kb * BK, a_row0 + m0, full);
+        tma_load_2d(dstA + A_STAGE_BYTES, &mapB, k_begin + kb * BK, a_row0 + n0, full);
     };
     int next_kb = kblocks < STAGES ? kblocks : STAGES;             // first k-block not yet requested (thread 0)
     if (threadIdx.x == 0) {
@@ -386,7 +417,7 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
         PB_CUDA(cudaEventRecord(e0, stream));
     }
     gemm_nt_kernel<CF><<<(unsigned)blocks, CF::THREADS, CF::SMEM_BYTES, stream>>>(
-        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only, tn); pb::note_launch();
+        mapA, mapB, C, ldc, (int)M, (int)N, (int)K, alpha, beta, lower_only, tn, GemmGroups{}); pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, stream));
         // algorithmic flops: 2MNK, or the lower triangle N(N+1)K for the SYRK form
@@ -396,7 +427,60 @@ int launch(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, c
     return PB_OK;
 }
 
+template <class CF>
+int launch_groups(cudaStream_t stream, const double* P, int64_t ldp, int64_t K, double alpha, double beta, double* c0,
+                  int64_t ldc, const GemmGroups& g, double flops) {
+    static PerDeviceOnce configured;
+    if (configured.first()) {
+        PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM_BYTES));
+        PB_CUDA(cudaFuncSetAttribute(gemm_nt_kernel<CF>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
+    }
+    CUtensorMap mapA, mapB;
+    PB_TRY(make_map(&mapA, P, g.R, K, ldp, CF::BM));
+    PB_TRY(make_map(&mapB, P, g.R, K, ldp, CF::BN));
+    const int tn = (int)ceil_div<int64_t>(g.nb, CF::BN);
+    int64_t blocks = 0;
+    for (int q = 0; q < g.count; ++q) blocks += ceil_div<int64_t>(g.R - (g.a0 + (int64_t)q * g.astep), CF::BM) * tn;
+    PB_CHECK(blocks > 0 && blocks < (1ll << 31), PB_ERR_INVALID, "gemm_nt_groups: bad tile count");
+    const bool prof = profiling_enabled() && CF::BM == 128;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        PB_CUDA(cudaEventCreate(&e0));
+        PB_CUDA(cudaEventCreate(&e1));
+        PB_CUDA(cudaEventRecord(e0, stream));
+    }
+    gemm_nt_kernel<CF><<<(unsigned)blocks, CF::THREADS, CF::SMEM_BYTES, stream>>>(
+        mapA, mapB, c0, ldc, 0, 0, (int)K, alpha, beta, 3, tn, g); pb::note_launch();
+    if (prof) {
+        PB_CUDA(cudaEventRecord(e1, stream));
+        profile_gemm(e0, e1, flops);
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
 }  // namespace
+
+// Grouped trailing update (see GemmGroups): for q < count,
+//   C_q[M_q x N_q] = alpha * P[a0 + q astep :, :K] P[a0 + q astep : +N_q, :K]^T + beta * C_q,  C_q = c0 + q cstep.
+int gemm_nt_groups(cudaStream_t stream, const double* P, int64_t ldp, int64_t R, int64_t K, double alpha, double beta,
+                   double* c0, int64_t ldc, int64_t cstep, int count, int64_t a0, int64_t astep, int64_t nb) {
+    if (count <= 0) return PB_OK;
+    PB_CHECK(K > 0 && alpha != 0.0 && nb > 0 && R < (1ll << 31) && a0 + (count - 1) * astep < R, PB_ERR_INVALID,
+             "gemm_nt_groups: bad arguments");
+    GemmGroups g;
+    g.count = count; g.R = (int)R; g.a0 = (int)a0; g.astep = (int)astep; g.nb = (int)nb; g.cstep = cstep;
+    double flops = 0;
+    int64_t tiles = 0;
+    for (int q = 0; q < count; ++q) {
+        const int64_t Mq = R - (a0 + q * astep), Nq = std::min<int64_t>(nb, Mq);
+        flops += 2.0 * Mq * (double)Nq * (double)K;
+        tiles += ceil_div<int64_t>(Mq, 128) * ceil_div<int64_t>(nb, 64);
+    }
+    if (tiles < 2 * num_sms()) return launch_groups<CfgSmall>(stream, P, ldp, K, alpha, beta, c0, ldc, g, flops);
+    return launch_groups<CfgMain>(stream, P, ldp, K, alpha, beta, c0, ldc, g, flops);
+}
 
 int gemm_nt(cudaStream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
             const double* B, int64_t ldb, double beta, double* C, int64_t ldc, bool lower_only) {

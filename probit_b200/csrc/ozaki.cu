@@ -1,0 +1,405 @@
+// FP64 contraction on the 5th-generation INT8 tensor cores (tcgen05.mma.kind::i8, TMEM accumulators, TMA-fed):
+//     C[M x N] += alpha * A[M x K] * B[N x K]^T        (row-major "NT", optionally only the lower tiles of a square C)
+// by error-free slicing (Ozaki scheme).  This is the trailing update of the Cholesky factorisation
+// (probit/implicit/Laplace.py:24 -> potrf.cu) past the 37 TFLOP/s wall of the FP64 DMMA pipe: tcgen05 has no f64 kind,
+// but the int8 kind runs at 4.5 POPS and its int32 accumulation is exact.
+//
+//   slicing   every row of an operand gets one exponent e (max |x| 2^-e in [1/4, 1/2)); the scaled row is cut into S = 7
+//             signed base-128 digits d_1 .. d_S in [-64, 64] by repeated round-to-nearest (each step exact in FP64):
+//             x = 2^e (sum_p d_p 128^-p + r 128^-S), |r| <= 1/2, i.e. 49 bits below the row's leading bit.
+//   products  A B^T = 2^(ea_i + eb_j) sum_{p,q} 128^-(p+q) (A_p B_q^T); every A_p B_q^T is an exact int8 x int8 -> int32
+//             GEMM.  Pairs are grouped by level t = p + q; levels t <= S + 1 are kept (28 products for S = 7, the
+//             dropped ones are below 128^-(S+2)), and the products of one level share one int32 TMEM accumulator.
+//   kernel    one CTA per 128 x 64 tile of C: warp 0 = TMA producer (3-D box: 64 K-bytes x rows x 7 planes, SWIZZLE_64B,
+//             two stages), warp 1 = MMA issuer (56 UTCIMMA per stage into 7 accumulators = 448 TMEM columns),
+//             warps 2..5 = epilogue (tcgen05.ld, int32 -> f64, level scaling by exact powers of two, row / column
+//             exponents, C += in FP64).
+// Accuracy: the slicing error is 2^-49 of each ROW's largest entry and the int32 sums are exact; a K = 1024 update of
+// O(1) entries is perturbed by ~1e-14 (DMMA: ~3e-15).  tests/test_gpu_kernels.py pins it against FP64 products and the
+// factorisation built on it against LAPACK.
+#include "common.cuh"
+#include <algorithm>
+
+namespace pb {
+
+namespace {
+
+constexpr int OZ_S = 7;                                  // slices per value; levels t = 2 .. S + 1
+constexpr int OZ_BM = 128, OZ_BN = 64, OZ_KC = 64;       // CTA tile; K bytes per stage (= one SWIZZLE_64B span)
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_A_PLANE = OZ_BM * OZ_KC, OZ_B_PLANE = OZ_BN * OZ_KC;
+constexpr int OZ_A_STAGE = OZ_S * OZ_A_PLANE, OZ_B_STAGE = OZ_S * OZ_B_PLANE;
+constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;        // 86016 B
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + 1024 /* align slack */ + 64 /* barriers */;
+constexpr int OZ_THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int OZ_TMEM_COLS = 512;
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both
+// K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "OZ_WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra OZ_WAIT_DONE;\n"
+        "bra OZ_WAIT_LOOP;\n"
+        "OZ_WAIT_DONE:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+        : "memory");
+}
+// K-major operand tile, rows at a 64-byte pitch, SWIZZLE_64B (cute::UMMA::SmemDescriptor): start address >> 4,
+// leading byte offset 1 (unused for swizzled K-major), stride byte offset = 8 rows x 64 B = 512 B >> 4, version 1,
+// layout type SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr) {
+    return (uint64_t)((addr >> 4) & 0x3fff) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ double pow2i(int e) {          // 2^e for -1022 <= e <= 1023; anything else -> NaN (bad row)
+    if (e < -1022 || e > 1023) return __longlong_as_double(0x7ff8000000000000ll);
+    return __hiloint2double((e + 1023) << 20, 0);
+}
+__device__ __forceinline__ void lower_tile_2to1(int bid, int& tm, int& tn) {   // tile row tm has column tiles 0 .. 2 tm + 1
+    int r = (int)((sqrtf(4.0f * bid + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) <= bid) ++r;
+    while (r * (r + 1) > bid) --r;
+    tm = r;
+    tn = bid - r * (r + 1);
+}
+
+// One warp per row: exponent + OZ_S digit planes.  planes[p][row][k] (K contiguous), expo[row].
+__global__ void __launch_bounds__(256)
+oz_slice_kernel(const double* __restrict__ P, int64_t rows, int K, int64_t ld, int8_t* __restrict__ planes,
+                int64_t plane_stride, int32_t* __restrict__ expo) {
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const double* p = P + row * ld;
+    double mx = 0.0;
+    bool bad = false;
+    for (int k = lane * 2; k < K; k += 64) {
+        const double2 v = *reinterpret_cast<const double2*>(p + k);
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+        bad |= !(fabs(v.x) <= 1.7976931348623157e308) || !(fabs(v.y) <= 1.7976931348623157e308);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    bad = __any_sync(0xffffffffu, bad);
+    int e = 0;
+    if (mx > 0.0) {
+        int q;
+        frexp(mx, &q);           // mx = m 2^q, m in [1/2, 1)
+        e = q + 1;               // |x| 2^-e < 1/2
+    }
+    // x 2^(7 - e) in (-64, 64); e is clamped so that the scale is a normal number (rows of denormals lose nothing that matters)
+    e = max(e, -900);
+    const double scale = pow2i(7 - e);
+    int8_t* out = planes + row * K;
+    for (int k = lane * 4; k < K; k += 128) {
+        const double2 v0 = *reinterpret_cast<const double2*>(p + k);
+        const double2 v1 = *reinterpret_cast<const double2*>(p + k + 2);
+        double t[4] = {v0.x * scale, v0.y * scale, v1.x * scale, v1.y * scale};
+#pragma unroll
+        for (int s = 0; s < OZ_S; ++s) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double d = rint(t[i]);
+                t[i] = (t[i] - d) * 128.0;                    // exact: |t - d| <= 1/2
+                word |= ((uint32_t)(__double2int_rn(d)) & 0xffu) << (8 * i);
+            }
+            *reinterpret_cast<uint32_t*>(out + (int64_t)s * plane_stride + k) = word;
+        }
+    }
+    if (lane == 0) expo[row] = bad ? 0x7fffffff : e;         // NaN / Inf in the row: poison the outputs it touches
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+               const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, double* __restrict__ C, int64_t ldc, int M,
+               int N, int K, double alpha, int lower_only) {
+    int tm, tn;
+    if (lower_only) lower_tile_2to1((int)blockIdx.x, tm, tn);
+    else { tm = (int)blockIdx.y; tn = (int)blockIdx.x; }
+    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+    if (m0 >= M || n0 >= N) return;                            // whole CTA, before any barrier / TMEM state exists
+
+    extern __shared__ uint8_t oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + OZ_STAGES * OZ_STAGE;         // full[0..1], empty[0..1], tmem_full
+    __shared__ uint32_t tmem_slot;
+    __shared__ double colscale[OZ_BN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = K / OZ_KC;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (OZ_STAGES + s), 1);
+        }
+        mbar_init(bars + 8 * 2 * OZ_STAGES, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(OZ_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2) {
+        const int j = threadIdx.x - 64;
+        if (j < OZ_BN) colscale[j] = (n0 + j < N) ? pow2i(eb[n0 + j]) : 0.0;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % OZ_STAGES;
+                if (kc >= OZ_STAGES) mbar_wait(bars + 8 * (OZ_STAGES + s), ((kc / OZ_STAGES) - 1) & 1);
+                const uint32_t full = bars + 8 * s;
+                mbar_expect_tx(full, OZ_STAGE);
+                tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
+                tma_load_3d(base + s * OZ_STAGE + OZ_A_STAGE, &mapB, kc * OZ_KC, n0, 0, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % OZ_STAGES;
+                mbar_wait(bars + 8 * s, (kc / OZ_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = base + s * OZ_STAGE, b0 = a0 + OZ_A_STAGE;
+#pragma unroll 1
+                for (int t = 2; t <= OZ_S + 1; ++t) {           // level t = p + q -> accumulator t - 2
+                    const uint32_t d = tmem + (uint32_t)(t - 2) * OZ_BN;
+                    for (int p = 1; p < t; ++p) {
+                        const int q = t - p;
+                        const uint64_t ad = oz_smem_desc(a0 + (p - 1) * OZ_A_PLANE);
+                        const uint64_t bd = oz_smem_desc(b0 + (q - 1) * OZ_B_PLANE);
+#pragma unroll
+                        for (int ks = 0; ks < OZ_KC / 32; ++ks)    // one UTCIMMA = 32 bytes of K: advance the start address
+                            oz_mma(d, ad + 2 * ks, bd + 2 * ks, (kc > 0 || p > 1 || ks > 0) ? 1u : 0u);
+                    }
+                }
+                oz_commit(bars + 8 * (OZ_STAGES + s));          // frees the stage once these MMAs have read it
+            }
+            oz_commit(bars + 8 * 2 * OZ_STAGES);                // accumulators complete
+        }
+    } else {
+        mbar_wait(bars + 8 * 2 * OZ_STAGES, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int quarter = warp & 3;                           // TMEM lanes this warp may touch: 32 (warp % 4) ..
+        const int64_t row = m0 + quarter * 32 + lane;
+        const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            double acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.0;
+#pragma unroll 1
+            for (int lvl = OZ_S - 1; lvl >= 0; --lvl) {         // least significant level first
+                uint32_t v[32];
+                const uint32_t addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(addr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                const double sc = pow2i(-7 * (lvl + 2));
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int)v[j], sc, acc[j]);
+            }
+            if (row < M) {
+                double* crow = C + row * ldc + n0 + half * 32;
+                const int col0 = n0 + half * 32;
+                const int lim = min(N, lower_only ? (int)min((int64_t)N, row + 1) : N) - col0;     // valid columns of this half
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    const double u0 = rs * colscale[half * 32 + j] * acc[j];
+                    const double u1 = rs * colscale[half * 32 + j + 1] * acc[j + 1];
+                    if (j + 1 < lim) {
+                        double2 c = *reinterpret_cast<double2*>(crow + j);
+                        c.x += u0;
+                        c.y += u1;
+                        *reinterpret_cast<double2*>(crow + j) = c;
+                    } else if (j < lim) {
+                        crow[j] += u0;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OZ_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn oz_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 3-D uint8 map over planes[S][rows][K]: box = 64 K-bytes x box_rows x S planes, SWIZZLE_64B, out-of-range rows read 0
+int oz_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t K, int64_t plane_stride, int box_rows) {
+    EncodeTiledFn enc = oz_encode();
+    PB_CHECK(enc != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)OZ_S};
+    cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, (cuuint32_t)OZ_S};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes) failed with %d (rows=%lld K=%lld)", (int)r,
+             (long long)rows, (long long)K);
+    return PB_OK;
+}
+
+int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const int8_t* Ap, const int32_t* ea,
+              int64_t a_rows, const int8_t* Bp, const int32_t* eb, int64_t b_rows, double* C, int64_t ldc, bool lower_only) {
+    static PerDeviceOnce configured;
+    if (configured.first())
+        PB_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    CUtensorMap mapA, mapB;
+    PB_TRY(oz_map(&mapA, Ap, M, K, a_rows * K, OZ_BM));
+    PB_TRY(oz_map(&mapB, Bp, N, K, b_rows * K, OZ_BN));
+    const int64_t tm = ceil_div<int64_t>(M, OZ_BM), tn = ceil_div<int64_t>(N, OZ_BN);
+    dim3 grid;
+    if (lower_only) {
+        PB_CHECK(tm * (tm + 1) < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
+        grid = dim3((unsigned)(tm * (tm + 1)), 1, 1);          // column tiles past N exit at once
+    } else {
+        PB_CHECK(tm < 65536, PB_ERR_INVALID, "ozaki: too many row tiles");
+        grid = dim3((unsigned)tn, (unsigned)tm, 1);
+    }
+    const bool prof = profiling_enabled();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        PB_CUDA(cudaEventCreate(&e0));
+        PB_CUDA(cudaEventCreate(&e1));
+        PB_CUDA(cudaEventRecord(e0, st));
+    }
+    oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
+                                                     lower_only ? 1 : 0); pb::note_launch();
+    if (prof) {
+        PB_CUDA(cudaEventRecord(e1, st));
+        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K);
+    }
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+int oz_slice(cudaStream_t st, const double* P, int64_t rows, int64_t K, int64_t ld, int8_t* planes, int32_t* expo) {
+    PB_CHECK((ld & 1) == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0, PB_ERR_INVALID, "ozaki: operand must be 16-byte aligned, ld even");
+    oz_slice_kernel<<<(unsigned)ceil_div<int64_t>(rows, 8), 256, 0, st>>>(P, rows, (int)K, ld, planes, rows * K, expo); pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+inline int64_t oz_align(int64_t b) { return (b + 255) / 256 * 256; }
+
+}  // namespace
+
+bool ozaki_supported(int64_t K) { return K >= OZ_KC && K % OZ_KC == 0 && K <= 65536; }
+
+int64_t ozaki_scratch_bytes(int64_t rows, int64_t K) { return oz_align(OZ_S * rows * K) + oz_align(4 * rows); }
+
+// C (lower tiles of the n x n matrix) += alpha * P P^T, P n x K (ld ldp)
+int ozaki_syrk_lower(cudaStream_t st, int64_t n, int64_t K, double alpha, const double* P, int64_t ldp, double* C,
+                     int64_t ldc, void* scratch, int64_t scratch_bytes) {
+    if (n <= 0) return PB_OK;
+    PB_CHECK(ozaki_supported(K), PB_ERR_INVALID, "ozaki: K must be a multiple of %d", OZ_KC);
+    PB_CHECK(scratch && scratch_bytes >= ozaki_scratch_bytes(n, K), PB_ERR_INVALID, "ozaki: scratch too small");
+    PB_CHECK((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, PB_ERR_INVALID, "ozaki: C must be 16-byte aligned, ld even");
+    int8_t* planes = reinterpret_cast<int8_t*>(scratch);
+    int32_t* expo = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(scratch) + oz_align(OZ_S * n * K));
+    PB_TRY(oz_slice(st, P, n, K, ldp, planes, expo));
+    return oz_launch(st, n, n, K, alpha, planes, expo, n, planes, expo, n, C, ldc, true);
+}
+
+// C[M x N] += alpha * A B^T, A M x K (lda), B N x K (ldb)
+int ozaki_gemm_nt(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+                  const double* B, int64_t ldb, double* C, int64_t ldc, void* scratch, int64_t scratch_bytes) {
+    if (M <= 0 || N <= 0) return PB_OK;
+    PB_CHECK(ozaki_supported(K), PB_ERR_INVALID, "ozaki: K must be a multiple of %d", OZ_KC);
+    const int64_t need = ozaki_scratch_bytes(M, K) + ozaki_scratch_bytes(N, K);
+    PB_CHECK(scratch && scratch_bytes >= need, PB_ERR_INVALID, "ozaki: scratch too small");
+    PB_CHECK((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, PB_ERR_INVALID, "ozaki: C must be 16-byte aligned, ld even");
+    uint8_t* s = reinterpret_cast<uint8_t*>(scratch);
+    int8_t* Ap = reinterpret_cast<int8_t*>(s);
+    int32_t* ea = reinterpret_cast<int32_t*>(s + oz_align(OZ_S * M * K));
+    uint8_t* s2 = s + ozaki_scratch_bytes(M, K);
+    int8_t* Bp = reinterpret_cast<int8_t*>(s2);
+    int32_t* eb = reinterpret_cast<int32_t*>(s2 + oz_align(OZ_S * N * K));
+    PB_TRY(oz_slice(st, A, M, K, lda, Ap, ea));
+    PB_TRY(oz_slice(st, B, N, K, ldb, Bp, eb));
+    return oz_launch(st, M, N, K, alpha, Ap, ea, M, Bp, eb, N, C, ldc, false);
+}
+
+}  // namespace pb
+
+extern "C" int64_t pb_ozaki_scratch_bytes(int64_t M, int64_t N, int64_t K) {
+    return pb::ozaki_scratch_bytes(M, K) + pb::ozaki_scratch_bytes(N, K);
+}
+
+extern "C" int pb_ozaki_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A,
+                                int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, int32_t lower_only,
+                                void* scratch, int64_t scratch_bytes) {
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (lower_only) {
+        PB_CHECK(M == N && A == B && lda == ldb, PB_ERR_INVALID, "ozaki: lower_only is the SYRK form (A == B, M == N)");
+        return pb::ozaki_syrk_lower(st, M, K, alpha, A, lda, C, ldc, scratch, scratch_bytes);
+    }
+    return pb::ozaki_gemm_nt(st, M, N, K, alpha, A, lda, B, ldb, C, ldc, scratch, scratch_bytes);
+}

@@ -210,6 +210,21 @@ int potrf_rec(const Ctx& c, double* A, int64_t n, int64_t col0) {
 
 }  // namespace
 
+// workspace = [leaf inverses | 256-block inverses and their transposes] (the solves read these) | slicing scratch of the
+// INT8 trailing update (n >= OZ_MIN_N only)
+constexpr int64_t OZ_MIN_N = 4096;
+int64_t potrf_inverse_bytes(int64_t n) {
+    const int64_t leaves = (n + LEAF - 1) / LEAF;
+    const int64_t blocks = (n + 255) / 256;
+    return ((leaves > 0 ? leaves : 1) * LEAF * LEAF + 2 * (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
+}
+int potrf_block_size(int64_t n);
+int64_t potrf_ozaki_bytes(int64_t n) { return n >= OZ_MIN_N ? ozaki_scratch_bytes(n, 1024) : 0; }
+static bool ozaki_enabled(int64_t n) {
+    const int mode = opts().potrf_ozaki;
+    return n >= OZ_MIN_N && (mode == 1 || (mode < 0 && n >= 8192));
+}
+
 int potrf_block_size(int64_t n) {
     const int forced = opt_potrf_nb();
     if (forced > 0) return forced / 64 * 64 > 0 ? forced / 64 * 64 : 64;
@@ -281,6 +296,10 @@ static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_
     }
 
     Ctx cs{side, lda, reinterpret_cast<double*>(workspace), info};
+    // trailing updates on the INT8 tensor cores: the slicing scratch sits behind the inverses in the workspace
+    const bool oz = ozaki_enabled(n) && ozaki_supported(NB) && NB <= 1024;
+    void* oz_scratch = reinterpret_cast<uint8_t*>(workspace) + potrf_inverse_bytes(n);
+    const int64_t oz_bytes = potrf_ozaki_bytes(n);
     EventPool pool;
     cudaEvent_t ev_panel, ev_trail = nullptr;
 
@@ -316,7 +335,10 @@ static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_
         // ---- main: the rest of the trailing update with panel k ----
         PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
         if (m2 > 0) {
-            PB_TRY(gemm_nt(stream, m2, m2, nb, -1.0, P2, lda, P2, lda, 1.0, A + k2 * lda + k2, lda, true));
+            if (oz && m2 >= 2048)
+                PB_TRY(ozaki_syrk_lower(stream, m2, nb, -1.0, P2, lda, A + k2 * lda + k2, lda, oz_scratch, oz_bytes));
+            else
+                PB_TRY(gemm_nt(stream, m2, m2, nb, -1.0, P2, lda, P2, lda, 1.0, A + k2 * lda + k2, lda, true));
             PB_TRY(pool.get(&ev_trail));
             PB_CUDA(cudaEventRecord(ev_trail, stream));
         }
@@ -492,9 +514,7 @@ int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, 
 extern "C" int64_t pb_potrf_workspace_bytes(int64_t n) {
     // [ceil(n/64) leaf inverses, 64x64] followed by [ceil(n/256) diagonal-block inverses, 256x256] and their
     // transposes (blas2.cu)
-    const int64_t leaves = (n + pb::LEAF - 1) / pb::LEAF;
-    const int64_t blocks = (n + 255) / 256;
-    return ((leaves > 0 ? leaves : 1) * pb::LEAF * pb::LEAF + 2 * (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
+    return pb::potrf_inverse_bytes(n) + pb::potrf_ozaki_bytes(n);
 }
 
 extern "C" int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,

@@ -1,6 +1,6 @@
 // Private layout of the caller-provided workspaces (fit.cu, dist.cu).
 //
-//  single GPU : K (n x ld) | factor buffer B | features Z | permuted features | 2 potrf workspaces | O(n) vectors | partials | scalars | info
+//  single GPU : K (n x ld) | factor buffer B | features Z | permuted features | potrf workspace | O(n) vectors | partials | scalars | info
 //  multi GPU  : the same slots, but `K` holds only this rank's rows [lo, hi) of the Gram matrix (nloc_max x ld) and
 //               `B` is the rank's share of the block-column-cyclic factor (n x ld_loc); three panel buffers, the
 //               leaf inverses of the owned panels and a panel-sized potrf workspace follow.  During the Newton
@@ -23,7 +23,7 @@ struct Layout {
     int64_t n = 0, ld = 0;
     int Dfmax = 0;
     // byte offsets
-    int64_t K = 0, B = 0, Z = 0, Zp = 0, potrf_ws = 0, potrf_ws2 = 0, vec = 0, partial = 0, scalars = 0, info = 0, total = 0;
+    int64_t K = 0, B = 0, Z = 0, Zp = 0, potrf_ws = 0, vec = 0, partial = 0, scalars = 0, info = 0, total = 0;
     int64_t vec_stride = 0;   // doubles per vector slot
     int64_t B_doubles = 0;    // capacity of the factor region
     // multi-GPU only
@@ -46,7 +46,6 @@ inline Layout make_layout(int64_t n, int D) {
     L.Z = take(n * (int64_t)L.Dfmax * 8);
     L.Zp = take((n + 1) * (int64_t)L.Dfmax * 8);
     L.potrf_ws = take(pb_potrf_workspace_bytes(n + 1));
-    L.potrf_ws2 = take(pb_potrf_workspace_bytes(n + 1));
     L.vec_stride = round_up(n + 1, 32);
     L.vec = take(L.vec_stride * V_COUNT * 8);
     L.partial = take(VEC_BLOCKS_MAX * 2 * 8);
@@ -106,7 +105,6 @@ struct Ws {
     double* B() const { return reinterpret_cast<double*>(base + L.B); }
     double* Z() const { return reinterpret_cast<double*>(base + L.Z); }
     void* potrf_ws() const { return base + L.potrf_ws; }
-    void* potrf_ws2() const { return base + L.potrf_ws2; }
     double* Zp() const { return reinterpret_cast<double*>(base + L.Zp); }
     double* dinv() const { return reinterpret_cast<double*>(base + L.potrf_ws); }
     double* vec(int slot) const { return reinterpret_cast<double*>(base + L.vec) + slot * L.vec_stride; }

@@ -106,6 +106,18 @@ def gemm_nt(A, B, C_out=None, alpha=1.0, beta=0.0, lower_only=False):
     return C_out
 
 
+def ozaki_gemm_nt(A, B, C_out, alpha=1.0, lower_only=False):
+    """C += alpha * A @ B.T on the INT8 tensor cores (error-free slicing, csrc/ozaki.cu); K must be a multiple of 64."""
+    lib = _lib.load()
+    M, K = A.shape
+    N = B.shape[0]
+    nbytes = lib.pb_ozaki_scratch_bytes(M, N, K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.pb_ozaki_gemm_nt(_stream(), M, N, K, float(alpha), _ptr(A), _ld(A), _ptr(B), _ld(B), _ptr(C_out),
+                                    _ld(C_out), int(lower_only), _ptr(scratch), nbytes))
+    return C_out
+
+
 class Factor:
     """In-place lower Cholesky factor plus the leaf-inverse workspace the solves need."""
 

@@ -301,7 +301,8 @@ def test_small_noise_negative_curvature_follows_the_reference_newton_iterates(se
     """log(Z + 1e-10) is not log-concave where Z <~ 1e-10 — with a small noise std, data 5.5 .. 8.7
     sigma outside their interval have h > 0 (up to ~9 / sigma^2).  The reference's LU Newton step (solvers.py:24) takes the
     indefinite Jacobian as it comes.  The CUDA path must follow the same iterates: tiny negative curvature is clamped,
-    materially negative curvature goes through the signed Cholesky (fit.cu indefinite_newton_solve).  Same weights as the
+    materially negative curvature goes through the block elimination of fit.cu indefinite_newton_solve (Cholesky of the
+    non-negative block, pivoted Gaussian elimination of the Schur complement).  Same weights as the
     oracle's literal LU iteration at the north-star tolerance, same iteration count.  (Where the reference itself fails
     to converge — it wanders for maxiter = 100 iterations and returns precisions of -1e3 — there is nothing to match.)"""
     from probit_b200 import approximators as PA, kernels as PK, utilities as PU
@@ -313,7 +314,11 @@ def test_small_noise_negative_curvature_follows_the_reference_newton_iterates(se
     gp = PA.LaplaceGP((X, y), make_prior(PK, family), PU.log_probit_likelihood)
     w, prec = gp.approximate_posterior(prm)
     assert gp.last_result.iterations == len(o.trace)
-    assert relerr(w.cpu().numpy(), w_ref) < TOL and relerr(prec.cpu().numpy(), p_ref) < TOL
+    assert relerr(w.cpu().numpy(), w_ref) < TOL
+    # the precision -h(f) is measured against its natural scale 1 / sigma^2: where Z ~ 1e-10 it moves by ~1e4 per unit of
+    # f (third derivative of log(Z + eps)), so weights equal to 1e-9 leave it equal to ~1e-7 of that scale, and entries
+    # that are themselves ~1e-10 (saturated data) carry no relative information at all
+    assert np.abs(prec.cpu().numpy() - p_ref).max() * sigma ** 2 < 1e-6
     if (p_ref > 0).all():                                         # predict needs K + P^-1 positive definite, as in the reference
         m, v = gp.predict(X[:20], prm, w, prec)
         m_ref, v_ref = o.predict(X[:20], prm, w_ref, p_ref)

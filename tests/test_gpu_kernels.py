@@ -71,6 +71,39 @@ def test_potrf_matches_lapack(n):
     assert relerr(Xd.cpu().numpy(), ref) < 1e-10
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 64, 128), (200, 150, 192), (1000, 333, 512), (4096, 4096, 1024)])
+def test_ozaki_int8_gemm_matches_fp64_product(M, N, K):
+    """csrc/ozaki.cu: C += alpha A B^T through 7 int8 digit planes on tcgen05 (UTCIMMA).  Entries span 12 orders of
+    magnitude across rows (each row has its own exponent) and 3 within a row; the error bound is 2^-49 of the row scales
+    times sqrt(K) (asserted with a factor-of-32 margin for the worst entry; observed 8 x at K = 512)."""
+    torch = _torch()
+    from probit_b200 import linalg
+    g = torch.Generator(device="cuda"); g.manual_seed(M + N + K)
+    A = linalg.empty_matrix(M, K); B = linalg.empty_matrix(N, K); Cm = linalg.empty_matrix(M, N)
+    A.copy_(torch.randn(M, K, generator=g, device="cuda", dtype=torch.float64) * torch.exp(3 * torch.randn(M, K, generator=g, device="cuda", dtype=torch.float64).clamp(-1, 1))
+            * (10.0 ** torch.randint(-6, 7, (M, 1), generator=g, device="cuda").double()))
+    B.copy_(torch.randn(N, K, generator=g, device="cuda", dtype=torch.float64) * (10.0 ** torch.randint(-3, 4, (N, 1), generator=g, device="cuda").double()))
+    A[M // 2].zero_()                                        # an all-zero row
+    C0 = torch.randn(M, N, generator=g, device="cuda", dtype=torch.float64)
+    Cm.copy_(C0)
+    linalg.ozaki_gemm_nt(A, B, Cm, alpha=-0.75)
+    ref = C0 - 0.75 * (A @ B.T)
+    scale = A.abs().amax(dim=1, keepdim=True) * B.abs().amax(dim=1, keepdim=True).T * (K ** 0.5) + C0.abs()
+    err = ((Cm - ref).abs() / scale).max().item()
+    assert err < 32 * 2.0 ** -49, err
+    # SYRK form: only tiles on / below the diagonal are touched
+    if M == N:
+        Cs = linalg.empty_matrix(M, M); Cs.copy_(C0)
+        linalg.ozaki_gemm_nt(A, A, Cs, alpha=1.0, lower_only=True)
+        ref = C0 + A @ A.T
+        sc = A.abs().amax(dim=1, keepdim=True) * A.abs().amax(dim=1, keepdim=True).T * (K ** 0.5) + C0.abs()
+        low = torch.tril(torch.ones(M, M, device="cuda", dtype=torch.bool))
+        assert (((Cs - ref).abs() / sc)[low]).max().item() < 32 * 2.0 ** -49
+        i = torch.arange(M, device="cuda")
+        untouched = (i[None, :] // 64) > (i[:, None] // 128) * 2 + 1          # column tiles right of the row tile's diagonal
+        assert torch.equal(Cs[untouched], C0[untouched])
+
+
 @pytest.mark.parametrize("n", [700, 3000, 5000])
 def test_potrf_graph_replay_is_bitwise_identical_to_eager(n):
     """pb_options.potrf_graph: the first call with a given set of buffers runs eagerly, the second captures the two-stream

@@ -29,7 +29,7 @@ def test_struct_layouts_match_the_header():
     assert ctypes.sizeof(_lib.KernelSpec) == 48
     assert ctypes.sizeof(_lib.LikelihoodSpec) == 40
     assert ctypes.sizeof(_lib.FitResult) == 48
-    assert ctypes.sizeof(_lib.Options) == 48
+    assert ctypes.sizeof(_lib.Options) == 56
     assert ctypes.sizeof(_lib.Problem) == 32 + 48 + 40
     assert _lib.Problem.kernel.offset == 32 and _lib.Problem.lik.offset == 80
 

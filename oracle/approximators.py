@@ -10,6 +10,11 @@ newton_form:
                  (what jax.jacobian of f_root materialises, solvers.py:23-24) + LU solve.
   "cholesky_B"  — the algebraically identical SPD form the CUDA path uses:
                  w+ = b - s*B^{-1}(s*K b), b = W f + g, s = sqrt(W), B = I + s s^T o K.
+  "signed_block" — the same step where some W < 0 (log(Z + 1e-10) is not log-concave for Z <~ 1e-10):
+                 w+ = b - S (D + S K S)^{-1} S K b, S = |W|^1/2, D = sign(W), solved by block elimination
+                 (Cholesky of the W >= 0 block, LU of the Schur complement) as fit.cu indefinite_newton_solve does.
+                 Algebraically identical to the LU step; the two are compared to MEASURE how reproducible the
+                 reference's own iterates are in that regime (tests/test_oracle_fit.py, tests/test_gpu_fit.py).
 """
 import numpy as np
 import scipy.linalg as sla
@@ -102,16 +107,39 @@ class LaplaceGP(Approximator):
         K = self._K(parameters[0])   # loop-invariant; the reference rebuilds it per evaluation (same values)
         y, lik = self.data[1], parameters[1]
         self.trace = []
+        self.negative_curvature = []
         z0 = np.zeros(self.N)
         if self.newton_form == "lu_jacobian":
             f = lambda z: self.grad_log_likelihood(K @ z, y, lik)
             jac = lambda z: self.hessian_log_likelihood(K @ z, y, lik)[:, None] * K
             return newton_solver(f, jac, z0, self.tolerance, self.maxiter, self.trace)
 
+        def signed_step(w, fm, g, W):
+            self.negative_curvature.append(int((W < 0).sum()))
+            S = np.sqrt(np.abs(W))
+            order = np.concatenate([np.flatnonzero(W >= 0), np.flatnonzero(W < 0)])   # stable partition
+            p = int((W >= 0).sum())
+            Sp, Kp = S[order], K[np.ix_(order, order)]
+            M = (Sp[:, None] * Kp) * Sp[None, :]
+            M[np.diag_indices(self.N)] += np.where(np.arange(self.N) < p, 1.0, -1.0)
+            b = W * fm + g
+            c = (S * (K @ b))[order]
+            L = np.linalg.cholesky(M[:p, :p]) if p else np.zeros((0, 0))
+            Yt = sla.solve_triangular(L, M[p:, :p].T, lower=True).T if p else np.zeros((self.N - p, 0))
+            z1 = sla.solve_triangular(L, c[:p], lower=True) if p else np.zeros(0)
+            x = np.empty(self.N)
+            x2 = np.linalg.solve(M[p:, p:] - Yt @ Yt.T, c[p:] - Yt @ z1) if p < self.N else np.zeros(0)
+            x[order[p:]] = x2
+            if p:
+                x[order[:p]] = sla.solve_triangular(L.T, z1 - Yt.T @ x2, lower=False)
+            return b - S * x
+
         def step(w):
             fm = K @ w
             g = self.grad_log_likelihood(fm, y, lik)
             W = -self.hessian_log_likelihood(fm, y, lik)
+            if self.newton_form == "signed_block":
+                return signed_step(w, fm, g, W)
             s = np.sqrt(W)
             Bm = np.eye(self.N) + (s[:, None] * K) * s[None, :]
             L = np.linalg.cholesky(Bm)

@@ -64,6 +64,8 @@ def parse():
     ap.add_argument("--mode", default="auto", choices=["auto", "single", "sharded"],
                     help="fit workload at N=1: `single` = LaplaceGP (default), `sharded` = the multi-GPU code path with one rank")
     ap.add_argument("--dist-block", type=int, default=0, help="panel width of the multi-GPU block-cyclic factorisation (0 = auto)")
+    ap.add_argument("--library-comparators", dest="library_sizes", default=None,
+                    help="internal: measure cuSOLVER potrf at these comma-separated sizes + cuBLAS DGEMM in THIS process, print JSON, exit")
     a = ap.parse_args()
     if a.n_test is None:
         a.n_test = 1000000 if a.workload == "predict" else 4096
@@ -379,6 +381,42 @@ def cublas_dgemm_tflops(torch, n=8192):
         return None
 
 
+def library_comparators_main(sizes):
+    """Child-process entry: the library kernels only (no product code is loaded).  One JSON line per finished measurement,
+    so that the parent keeps what completed if a library kernel faults."""
+    import torch
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    print(json.dumps({"cublas_dgemm_8192_tflops": cublas_dgemm_tflops(torch)}), flush=True)
+    for n in sizes:
+        print(json.dumps({"potrf_tflops_cusolverDnDpotrf": cusolver_potrf_tflops(torch, [n])}), flush=True)
+
+
+def library_comparators(sizes, timeout=600):
+    """cuSOLVER / cuBLAS measured in a CHILD process on the same GPU, after the product's own measurements: a fault inside
+    a library kernel (observed: cusolverDnXpotrf at n = 65536 raised an illegal memory access on this image, which
+    poisons the CUDA context of whoever called it) must not cost the bench its line."""
+    import subprocess
+    out = {"potrf_tflops_cusolverDnDpotrf": {}, "cublas_dgemm_8192_tflops": None}
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--library-comparators", ",".join(str(n) for n in sizes)],
+                           capture_output=True, text=True, timeout=timeout)
+        for ln in r.stdout.splitlines():
+            try:
+                d = json.loads(ln)
+            except ValueError:
+                continue
+            if "cublas_dgemm_8192_tflops" in d:
+                out["cublas_dgemm_8192_tflops"] = d["cublas_dgemm_8192_tflops"]
+            out["potrf_tflops_cusolverDnDpotrf"].update(d.get("potrf_tflops_cusolverDnDpotrf", {}))
+        missing = [n for n in sizes if str(n) not in out["potrf_tflops_cusolverDnDpotrf"]]
+        if r.returncode != 0 or missing:
+            tail = (r.stderr or "").strip().splitlines()[-1:] or [""]
+            out["potrf_tflops_cusolverDnDpotrf"]["error"] = f"child rc={r.returncode}, no result for n={missing}: {tail[0][:160]}"
+    except Exception as exc:      # comparator only: its absence must not fail the bench
+        out["potrf_tflops_cusolverDnDpotrf"]["error"] = repr(exc)[:200]
+    return out
+
+
 def our_potrf_tflops(torch, lib, sizes, options=None):
     from probit_b200 import linalg
     out = {}
@@ -580,11 +618,15 @@ def bench_fit(args, env):
         line["restarts"] = restarts
     if world == 1 and not args.no_comparators:
         sizes = [16384, 32768] + ([65536] if n >= 65536 else [])
+        ours = our_potrf_tflops(torch, lib, sizes)
+        torch.cuda.empty_cache()
+        libs = library_comparators(sizes)
         line["comparators"] = {
-            "what": "library kernels on the same GPU in the same process (dlopen in bench.py only; the product links neither)",
-            "potrf_tflops_ours": our_potrf_tflops(torch, lib, sizes),
-            "potrf_tflops_cusolverDnDpotrf": cusolver_potrf_tflops(torch, sizes),
-            "cublas_dgemm_8192_tflops": cublas_dgemm_tflops(torch),
+            "what": ("library kernels on the same GPU, measured right after the product's own in a child process of bench.py "
+                     "(dlopen there only; the product links neither)"),
+            "potrf_tflops_ours": ours,
+            "potrf_tflops_cusolverDnDpotrf": libs["potrf_tflops_cusolverDnDpotrf"],
+            "cublas_dgemm_8192_tflops": libs["cublas_dgemm_8192_tflops"],
             "fp64_tensor_peak_tflops": peak,
         }
     if not args.no_cpu_baseline and world == 1:
@@ -714,7 +756,9 @@ def run_ours(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.library_sizes is not None:
+        library_comparators_main([int(x) for x in a.library_sizes.split(",") if x])
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)

@@ -3,9 +3,9 @@
 set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-OUT=../libprobit_b200.so
+OUT=${PB_OUT:-../libprobit_b200.so}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr -Wno-deprecated-gpu-targets"
-OBJ=../../build/obj
+OBJ=${PB_OBJ:-../../build/obj}
 mkdir -p $OBJ
 SRCS="capi gemm_dmma ozaki potrf likelihood gram blas2 fit dist"
 pids=""

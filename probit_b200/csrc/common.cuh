@@ -118,24 +118,33 @@ __device__ __forceinline__ double block_sum(double v) {
 // kernels are issue bound on FP64 transcendentals: ncu sm__throughput 74-76 %).
 // Cody-Waite reduction with fdlibm's ln2 split, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
 // 4e-18), exponent added directly to the high word; returns 0 for x > 707 (e^-707 = 8e-308).  <= 2 ulp.
+// The coefficients live in the constant bank: as FP64 immediates ptxas re-materialises every one of them with two UMOVs
+// in front of each DFMA (the Gram kernel spent 40 % of its issue slots on that); a constant-bank operand costs nothing.
+__constant__ double EXP_NEG_C[14] = {
+    1.6059043836821613e-10,   // 1/13!
+    2.08767569878681e-09,     // 1/12!
+    2.505210838544172e-08,    // 1/11!
+    2.755731922398589e-07,    // 1/10!
+    2.7557319223985893e-06,   // 1/9!
+    2.48015873015873e-05,     // 1/8!
+    1.984126984126984e-04,    // 1/7!
+    1.388888888888889e-03,    // 1/6!
+    8.333333333333333e-03,    // 1/5!
+    4.1666666666666664e-02,   // 1/4!
+    1.6666666666666666e-01,   // 1/3!
+    1.4426950408889634,       // log2 e
+    -6.93147180369123816490e-01,   // -ln2_hi
+    -1.90821492927058770002e-10};  // -ln2_lo
 __device__ __forceinline__ double exp_neg(double x) {
     const double MAGIC = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
-    const double t = fma(-x, 1.4426950408889634, MAGIC);
+    const double t = fma(-x, EXP_NEG_C[11], MAGIC);
     const int n = __double2loint(t);                          // n = round(-x log2 e) <= 0
     const double nf = t - MAGIC;
-    double r = fma(nf, -6.93147180369123816490e-01, -x);      // -x - n ln2_hi (exact product)
-    r = fma(nf, -1.90821492927058770002e-10, r);              //      - n ln2_lo
-    double p = 1.6059043836821613e-10;                        // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                      // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                     // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                     // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                    // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                      // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                     // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                     // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                     // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                    // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                    // 1/3!
+    double r = fma(nf, EXP_NEG_C[12], -x);                    // -x - n ln2_hi (exact product)
+    r = fma(nf, EXP_NEG_C[13], r);                            //      - n ln2_lo
+    double p = EXP_NEG_C[0];
+#pragma unroll
+    for (int j = 1; j <= 10; ++j) p = fma(p, r, EXP_NEG_C[j]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);

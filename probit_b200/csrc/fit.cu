@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256)
 laplace_prep_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
                     const void* __restrict__ y, int64_t n, double neg_floor, double* __restrict__ s,
                     double* __restrict__ b, double* __restrict__ Wout, double* __restrict__ partial) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, bad = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256)
 posterior_stats_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f,
                        const void* __restrict__ y, const double* __restrict__ w, int64_t n, double* __restrict__ prec,
                        double* __restrict__ partial) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
     lik::stage_cutpoints(p, cut, sc);
     double sum_ll = 0, ftw = 0;
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
@@ -96,7 +96,7 @@ posterior_stats_kernel(lik::Params p, const double* __restrict__ cut, const doub
 __global__ void __launch_bounds__(256)
 vb_rhs_kernel(lik::Params p, const double* __restrict__ cut, const double* __restrict__ f, const void* __restrict__ y,
               int64_t n, double* __restrict__ r) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
     lik::stage_cutpoints(p, cut, sc);
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
         const double fi = f[i];
@@ -297,11 +297,11 @@ __global__ void __launch_bounds__(256)
 ordinal_param_grad_kernel(const double* __restrict__ f, const long long* __restrict__ y, const double* __restrict__ cut,
                           int J, double sigma, double eps, const double* __restrict__ V, const double* __restrict__ uvec,
                           int64_t n, double* __restrict__ partial) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
     __shared__ double acc[lik::MAX_CUT + 2];
     for (int i = threadIdx.x; i <= J; i += 256) sc[i] = cut[i];
-    for (int i = threadIdx.x; i < lik::NCDF_DOUBLES; i += 256) sc[lik::MAX_CUT + 1 + i] = lik::NCDF_TABLE[i];
-    const double* tbl = sc + lik::MAX_CUT + 1;
+    lik::stage_tables(sc);
+    const double* tbl = sc + lik::TBL_OFF;
     for (int i = threadIdx.x; i < J + 2; i += 256) acc[i] = 0.0;
     __syncthreads();
     for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {

@@ -14,41 +14,92 @@ namespace pb {
 
 namespace {
 
+// One datum per thread, the batch of latent vectors in the inner loop: the datum's label, its two cutpoints and their
+// finiteness are resolved once and 1 / sigma comes in through the parameters, so an element costs one 8-byte load, the
+// arithmetic and one 8-byte store per requested output (no index division, no gather).  blockIdx.y strides over the
+// batch; the next element's load is issued before the current one is evaluated.  KIND is a compile-time constant so
+// the ordinal path carries none of the safe-mode / Gaussian code (registers, instruction cache).
+template <int KIND>
 __global__ void __launch_bounds__(256)
-likelihood_kernel(lik::Params p, const double* __restrict__ f, const void* __restrict__ yv, int64_t n, int64_t total,
+likelihood_kernel(lik::Params p, const double* __restrict__ f, const void* __restrict__ yv, int64_t n, int64_t batch,
                   const double* __restrict__ cut, double* __restrict__ ll, double* __restrict__ g,
                   double* __restrict__ h, double* __restrict__ d3) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
     lik::stage_cutpoints(p, cut, sc);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t d = (total == n) ? i : i % n;
-        const lik::Out o = lik::eval(p, f[i], yv, d, sc);
+    const int64_t d = blockIdx.x * 256ll + threadIdx.x;
+    if (d >= n) return;
+    const double* tbl = sc + lik::TBL_OFF;
+    double b1 = 0.0, b2 = 0.0, yg = 0.0;
+    if (KIND == PB_LIK_GAUSSIAN) {
+        yg = reinterpret_cast<const double*>(yv)[d];
+    } else {
+        long long yi = reinterpret_cast<const long long*>(yv)[d];
+        yi = yi < 0 ? 0 : (yi >= p.J ? p.J - 1 : yi);     // JAX clamps out-of-range gather indices
+        b1 = sc[yi];
+        b2 = sc[yi + 1];
+    }
+    const bool fin1 = b1 != -INFINITY, fin2 = b2 != INFINITY;
+    const double is = 1.0 / p.sigma;
+    const int64_t step = (int64_t)gridDim.y * n;
+    int64_t i = (int64_t)blockIdx.y * n + d;
+    const int64_t total = batch * n;
+    double fi = i < total ? f[i] : 0.0;
+    for (; i < total; i += step) {
+        const double fnext = i + step < total ? f[i + step] : 0.0;
+        lik::Out o;
+        if (KIND == PB_LIK_GAUSSIAN) o = lik::gaussian(fi, yg, p.sigma);
+        else if (KIND == PB_LIK_ORDINAL_PROBIT) {
+            if (d3) o = lik::ordinal_core<true, true>(fi, b1, b2, fin1, fin2, is, p.eps, tbl);
+            else if (ll) o = lik::ordinal_core<true, false>(fi, b1, b2, fin1, fin2, is, p.eps, tbl);
+            else o = lik::ordinal_core<false, false>(fi, b1, b2, fin1, fin2, is, p.eps, tbl);
+        } else o = lik::ordinal_safe(fi, b1, b2, p.sigma, p.eps, p.ub, p.ub2, p.ub3, tbl);
         if (ll) ll[i] = o.ll;
         if (g) g[i] = o.g;
         if (h) h[i] = o.h;
         if (d3) d3[i] = o.d3;
+        fi = fnext;
     }
 }
 
 // probit_predictive_distributions (probit/utilities.py:232-249): out[i][j] = probit(s_i, b_j, b_{j+1}, m_i),
-// s_i = sqrt(var_i + sigma^2); one thread per test point writes its J probabilities.
+// s_i = sqrt(var_i + sigma^2).  One thread per test point: one reciprocal square root, then Phi at each finite cutpoint
+// (branch-free table evaluation, likelihood.cuh) — the J + 1 divisions and the sqrt of the literal expression were half
+// of the instructions.  STAGED: the CTA's 256 x J probabilities are one contiguous block of `out`, so they go through
+// shared memory and leave as full 128-byte lines instead of J strided 8-byte stores per thread.
+template <bool STAGED>
 __global__ void __launch_bounds__(256)
 predictive_kernel(const double* __restrict__ mean, const double* __restrict__ var, int64_t n,
                   const double* __restrict__ cut, int J, double sigma, double* __restrict__ out) {
-    __shared__ double sc[lik::SMEM_DOUBLES];
+    PB_LIK_SMEM(sc);
+    extern __shared__ __align__(16) double stage[];               // STAGED: 256 x J
     for (int i = threadIdx.x; i <= J; i += blockDim.x) sc[i] = cut[i];
-    for (int i = threadIdx.x; i < lik::NCDF_DOUBLES; i += blockDim.x) sc[lik::MAX_CUT + 1 + i] = lik::NCDF_TABLE[i];
+    lik::stage_tables(sc);
     __syncthreads();
-    const double* tbl = sc + lik::MAX_CUT + 1;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double m = mean[i];
-        const double s = sqrt(var[i] + sigma * sigma);
-        double lo = (sc[0] == -INFINITY) ? 0.0 : lik::norm_cdf((sc[0] - m) / s, tbl);     // utilities.py:219-221
-        for (int j = 0; j < J; ++j) {
-            const double b2 = sc[j + 1];
-            const double hi = (b2 == INFINITY) ? 1.0 : lik::norm_cdf((b2 - m) / s, tbl);  // utilities.py:222-224
-            out[i * J + j] = hi - lo;
-            lo = (b2 == -INFINITY) ? 0.0 : hi;
+    const double* tbl = sc + lik::TBL_OFF;
+    const double s2 = sigma * sigma;
+    for (int64_t base = blockIdx.x * 256ll; base < n; base += (int64_t)gridDim.x * 256) {
+        const int64_t i = base + threadIdx.x;
+        if (i < n) {
+            const double m = mean[i];
+            const double rs = rsqrt(var[i] + s2);
+            double* dst = STAGED ? stage + threadIdx.x * J : out + i * J;
+            // infinite cutpoints are 0 / 1 whatever the moments (the jnp.where guards of utilities.py:219-224); the
+            // test is on the cutpoints, so it is uniform across the warp
+            double lo = sc[0] == -INFINITY ? 0.0 : lik::norm_cdf((sc[0] - m) * rs, tbl);
+            for (int j = 0; j < J; ++j) {
+                const double b2 = sc[j + 1];
+                const double hi = b2 == INFINITY ? 1.0 : lik::norm_cdf((b2 - m) * rs, tbl);
+                dst[j] = hi - lo;
+                lo = b2 == -INFINITY ? 0.0 : hi;
+            }
+        }
+        if (STAGED) {
+            __syncthreads();
+            const int64_t rows = n - base < 256 ? n - base : 256;
+            const int count = (int)rows * J;
+            double* gout = out + base * J;
+            for (int e = threadIdx.x; e < count; e += 256) gout[e] = stage[e];
+            __syncthreads();
         }
     }
 }
@@ -62,10 +113,19 @@ int likelihood(cudaStream_t stream, const pb_likelihood_spec& spec, const double
     if (total == 0) return PB_OK;
     lik::Params p;
     PB_TRY(lik::make_params(spec, p));
-    const int64_t want = ceil_div<int64_t>(total, 256);
+    const int64_t gx = ceil_div<int64_t>(n, 256);
+    PB_CHECK(gx < (1ll << 31), PB_ERR_INVALID, "likelihood: n too large");
     const int64_t cap = (int64_t)num_sms() * 8;
-    likelihood_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p, f, y, n, total, spec.cutpoints, ll, g,
-                                                                               h, d3); pb::note_launch();
+    int64_t gy = ceil_div<int64_t>(cap, gx);
+    gy = gy < 1 ? 1 : (gy > batch ? batch : (gy > 65535 ? 65535 : gy));
+    const dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    if (p.kind == PB_LIK_GAUSSIAN)
+        likelihood_kernel<PB_LIK_GAUSSIAN><<<grid, 256, 0, stream>>>(p, f, y, n, batch, spec.cutpoints, ll, g, h, d3);
+    else if (p.kind == PB_LIK_ORDINAL_PROBIT)
+        likelihood_kernel<PB_LIK_ORDINAL_PROBIT><<<grid, 256, 0, stream>>>(p, f, y, n, batch, spec.cutpoints, ll, g, h, d3);
+    else
+        likelihood_kernel<PB_LIK_ORDINAL_PROBIT_SAFE><<<grid, 256, 0, stream>>>(p, f, y, n, batch, spec.cutpoints, ll, g, h, d3);
+    pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }
@@ -79,8 +139,14 @@ extern "C" int pb_predictive_distributions(pb_stream_t stream, const pb_likeliho
     if (n_test == 0) return PB_OK;
     const int64_t want = pb::ceil_div<int64_t>(n_test, 256);
     const int64_t cap = (int64_t)pb::num_sms() * 8;
-    pb::predictive_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        mean, variance, n_test, lik->cutpoints, lik->J, lik->sigma, out); pb::note_launch();
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (lik->J <= 16)
+        pb::predictive_kernel<true><<<grid, 256, 256 * lik->J * sizeof(double), st>>>(mean, variance, n_test, lik->cutpoints,
+                                                                                      lik->J, lik->sigma, out);
+    else
+        pb::predictive_kernel<false><<<grid, 256, 0, st>>>(mean, variance, n_test, lik->cutpoints, lik->J, lik->sigma, out);
+    pb::note_launch();
     PB_CUDA(cudaGetLastError());
     return PB_OK;
 }

@@ -303,8 +303,9 @@ def test_small_noise_negative_curvature_follows_the_reference_newton_iterates(se
     materially negative curvature goes through the block elimination of fit.cu indefinite_newton_solve (Cholesky of the
     non-negative block, pivoted Gaussian elimination of the Schur complement).
 
-    * reproducible cases (two orderings of the reference's own arithmetic agree, tests/test_oracle_fit.py): same
-      iteration count, weights at the north-star 1e-8;
+    * reproducible cases (a re-ordering of the reference's linear algebra and a 1-ulp-equivalent Phi both leave its
+      answer unchanged, tests/test_oracle_fit.py): same iteration count, weights at the north-star 1e-8 ("weights" cases:
+      the variants reach one fixed point in different numbers of steps, so only the weights are held);
     * the others (knife-edge stopping test; chaotic wandering between several fixed points): the reference has no single
       answer, so the product is held to what every run of the reference satisfies — it converges, and its result
       is a fixed point of the reference's map: one more LITERAL reference Newton step (oracle, LU) moves it by <= tol.
@@ -328,7 +329,8 @@ def test_small_noise_negative_curvature_follows_the_reference_newton_iterates(se
     assert np.abs(prec + h).max() * sigma ** 2 < 1e-5
     if not reproducible:
         return
-    assert gp.last_result.iterations == len(o.trace)
+    if reproducible is True:                                      # "weights": same fixed point, the count is not defined
+        assert gp.last_result.iterations == len(o.trace)
     assert relerr(w, w_ref) < TOL
     assert np.abs(prec - p_ref).max() * sigma ** 2 < 1e-5
     if (p_ref > 0).all():                                         # predict needs K + P^-1 positive definite, as in the reference

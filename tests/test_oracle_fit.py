@@ -49,36 +49,55 @@ def test_gaussian_laplace_is_exact_gp_regression():
     assert np.allclose(m, Ks.T @ wc) and np.allclose(v, params[0][1] - np.einsum("ij,ij->j", Ks, np.linalg.solve(K + s2 * np.eye(20), Ks)))
 
 
-NEGATIVE_CURVATURE_CASES = [  # seed, N, D, J, family, sigma, reproducible?   (shared with tests/test_gpu_fit.py)
-    (17, 257, 1, 3, "eq", 0.08, True), (21, 400, 2, 4, "matern12", 0.12, True), (26, 400, 2, 4, "matern12", 0.12, True),
-    (27, 300, 1, 3, "eq", 0.1, True), (4, 600, 3, 4, "eq", 0.18, True),
+# seed, N, D, J, family, sigma, reproducible?   (shared with tests/test_gpu_fit.py)
+#   True      : iteration count and weights survive a re-ordering of the linear algebra AND a 1-ulp change of Phi
+#   "weights" : every variant reaches the same fixed point (weights to 1e-9) but the iteration count moves
+#   False     : knife-edge stopping test or chaotic wandering between several fixed points: no single reference answer
+NEGATIVE_CURVATURE_CASES = [
+    (17, 257, 1, 3, "eq", 0.08, True), (21, 400, 2, 4, "matern12", 0.12, True), (4, 600, 3, 4, "eq", 0.18, True),
+    (26, 400, 2, 4, "matern12", 0.12, "weights"),   # 31 iterations, 32 with Phi = erfc(-z / sqrt 2) / 2: same fixed point
+    (27, 300, 1, 3, "eq", 0.1, False),        # 51 / 74 / 90 iterations for three 1-ulp-equivalent Phi, two different fixed points
     (9, 500, 1, 5, "eq", 0.1, False),         # last step 9.5e-6 vs tol 1e-5: the iteration count is a coin toss (7 or 8)
     (3, 350, 1, 3, "matern12", 0.1, False)]   # wanders for ~35 steps and lands on DIFFERENT fixed points (rel. diff 0.3)
 
 
 @pytest.mark.parametrize("seed,N,D,J,family,sigma,reproducible", NEGATIVE_CURVATURE_CASES)
 def test_signed_block_form_and_how_reproducible_the_reference_is_with_negative_curvature(seed, N, D, J, family, sigma,
-                                                                                         reproducible):
+                                                                                         reproducible, monkeypatch):
     """With a small noise std, log(Z + 1e-10) has positive second derivative where Z <~ 1e-10 and the reference's LU step
     (solvers.py:24) walks through indefinite Jacobians.  The signed block elimination (what fit.cu does) is the same
-    step algebraically.  Where the two agree the reference's answer is REPRODUCIBLE and the CUDA path is held to it at
-    1e-8; where two orderings of the same arithmetic already disagree (knife-edge stopping test, or chaotic wandering
-    between several fixed points) there is no single reference answer to hold anything to — measured here."""
+    step algebraically, and the CUDA likelihood's Phi is the reference's up to ~1 ulp.  Where Z ~ 1e-10 the Hessian is
+    defined to ~1e-6 relative only (1e-16 of rounding in a Phi difference divided by Z + 1e-10), so an iteration that
+    wanders for tens of steps amplifies exactly those differences.  Three variants of the reference's own arithmetic are
+    run here — the literal LU form, the signed block form, and the LU form with Phi(z) = erfc(-z / sqrt 2) / 2 in place
+    of (1 + erf(z / sqrt 2)) / 2 (utilities.py:18-19), a 1-ulp-equivalent expression — and the case is classified by
+    what survives: where all agree the reference's answer is REPRODUCIBLE and the CUDA path is held to it at 1e-8;
+    otherwise there is no single reference answer for that quantity and the CUDA path is held to what every variant
+    satisfies (convergence to a fixed point of the reference's map)."""
+    from scipy.special import erfc
     X, y, params, family = ordinal_problem(seed, N, D, J, family)
     prm = (params[0], (sigma, params[1][1]))
     a = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood)
     b = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood, newton_form="signed_block")
     wa, _ = a.approximate_posterior(prm)
     wb, _ = b.approximate_posterior(prm)
-    assert max(b.negative_curvature) > 0                      # the indefinite step is exercised
-    assert len(a.trace) < 100 and len(b.trace) < 100          # both converge
-    if reproducible:
-        assert len(a.trace) == len(b.trace) and relerr(wb, wa) < 1e-9
-    else:
-        assert len(a.trace) != len(b.trace)
-    # either way the result is a fixed point of the reference's map: one more literal Newton step moves it by <= tol
     K = a._K(prm[0])
-    for w in (wa, wb):
+    with monkeypatch.context() as mp_:
+        mp_.setattr(OU, "ndtr", lambda z: 0.5 * erfc(-z / OU.sqrt_2))
+        c = OA.LaplaceGP((X, y), make_prior(OK, family), OU.log_probit_likelihood)
+        wc, _ = c.approximate_posterior(prm)
+    assert max(b.negative_curvature) > 0                      # the indefinite step is exercised
+    counts = {len(a.trace), len(b.trace), len(c.trace)}
+    assert max(counts) < 100                                  # every variant converges
+    same_point = relerr(wb, wa) < 5e-9 and relerr(wc, wa) < 5e-9
+    if reproducible is True:
+        assert len(counts) == 1 and same_point
+    elif reproducible == "weights":
+        assert len(counts) > 1 and same_point
+    else:
+        assert len(counts) > 1
+    # either way the result is a fixed point of the reference's map: one more literal Newton step moves it by <= tol
+    for w in (wa, wb, wc):
         fm = K @ w
         g, h = OU.grad_log_probit_likelihood_autodiff(fm, y, prm[1]), OU.hessian_log_probit_likelihood_autodiff(fm, y, prm[1])
         step = np.linalg.solve(h[:, None] * K - np.eye(N), g - w)

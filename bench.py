@@ -297,6 +297,18 @@ def make_inputs(env, n, n_test):
     return X, y, cut, Xs
 
 
+def measured_bf16_sustained():
+    """Dense bf16 TFLOP/s of this pool's B200 under a seconds-long load (driver-written MEASURED_PEAKS.json), else the
+    profiling recipe's fallback."""
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+    except Exception:
+        return 1400.0, "fallback 1400 TFLOP/s sustained bf16 (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
 def measure_peak(lib):
     peak = C.c_double(0)
     if lib.pb_measure_fp64_tensor_peak(C.byref(peak)) == 0 and peak.value > 0:
@@ -524,6 +536,8 @@ def bench_fit(args, env):
     ms_res, out = env.timed(step_resident, args.steps)
     n_l, g_ms, g_fl = C.c_longlong(0), C.c_double(0), C.c_double(0)
     lib.pb_profile_end(C.byref(n_l), C.byref(g_ms), C.byref(g_fl))
+    n8, ms8, fl8 = C.c_longlong(0), C.c_double(0), C.c_double(0)
+    lib.pb_profile_int8(C.byref(n8), C.byref(ms8), C.byref(fl8))
     launches = lib.pb_launch_count() - launches0
     clocks = sampler.stop()
     iterations = gp.last_result.iterations
@@ -577,6 +591,34 @@ def bench_fit(args, env):
 
     peak, peak_src = measure_peak(lib)
     achieved = g_fl.value / g_ms.value * 1e-9 if g_ms.value > 0 else None
+    dmma_roofline = {
+        "bound": "tensor", "kernel": "gemm_nt_kernel<128x64, 8 warps, 2 CTA/SM> (FP64 DMMA: panel work, K < 1024 updates, TRSM leaves)",
+        "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+        "traffic": 3.03e9, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch of this kernel "
+                                            "(SYRK 16384 x 512, algorithmic 2.21e9 B; profiles/r01_gemm_main_ncu.md); the kernel is "
+                                            "tensor-bound, launches in the timed region vary in shape"),
+        "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
+        "algorithmic_flops_per_step": g_fl.value / args.steps,
+        "note": "rank 0's launches" if world > 1 else None,
+    }
+    int8_roofline = None
+    if ms8.value > 0:
+        bf16, bf16_src = measured_bf16_sustained()
+        tops = 28.0 * fl8.value / ms8.value * 1e-9           # every launch is 28 exact int8 GEMMs of its M x N x K shape
+        int8_roofline = {
+            "bound": "tensor", "kernel": ("oz_gemm_kernel (tcgen05.mma kind::i8 into 7 TMEM accumulators, TMA-fed): FP64 contraction by "
+                                          "error-free slicing into 7 int8 digit planes, 28 int8 GEMMs per FP64 GEMM"),
+            "achieved": tops, "peak": 2.0 * bf16, "unit": "TFLOP/s", "frac": tops / (2.0 * bf16),
+            "ops": "int8 multiply-add = 2 ops; achieved = 28 x 2 M N K per launch / CUDA-event time of the launch",
+            "fp64_equivalent_tflops": fl8.value / ms8.value * 1e-9,
+            "fp64_equivalent_vs_dmma_peak": fl8.value / ms8.value * 1e-9 / peak,
+            "traffic": 628e6, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch (SYRK 8192 x 1024 lower: "
+                                               "algorithmic 596e6 B = digit planes once + C read-modify-write; profiles/r02_oz_gemm_ncu.md)"),
+            "launches": int(n8.value), "kernel_ms_total": ms8.value,
+            "peak_source": "2 x " + bf16_src + " (tcgen05 kind::i8 issues at twice the bf16 rate: ncu peak_sustained 16384 vs 8192 ops/clk/SM)",
+            "algorithmic_flops_per_step": fl8.value / args.steps,
+            "note": "rank 0's launches" if world > 1 else None,
+        }
     n_potrf = fit_factorizations + 1           # + the factorisation of B(w*) that predict needs
     line = {
         "metric": METRIC, "value": sec_res, "unit": "s", "n_gpus": world, "steps": args.steps,
@@ -600,17 +642,11 @@ def bench_fit(args, env):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "stages": stages,
-        "roofline": {
-            "bound": "tensor", "kernel": "gemm_nt_kernel<128x64, 8 warps, 2 CTA/SM> (Cholesky trailing update / TRSM / predict solve)",
-            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
-            "traffic": 3.03e9, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch of this kernel "
-                                                "(SYRK 16384 x 512, algorithmic 2.21e9 B; profiles/r01_gemm_main_ncu.md); the kernel is "
-                                                "tensor-bound, launches in the timed region vary in shape"),
-            "launches": int(n_l.value), "kernel_ms_total": g_ms.value, "peak_source": peak_src,
-            "algorithmic_flops_per_step": g_fl.value / args.steps,
-            "note": "rank 0's launches" if world > 1 else None,
-        },
+        # the kernel that takes most of the step: the INT8-sliced contraction when it is on (n >= 8192), else the DMMA GEMM
+        "roofline": int8_roofline if (int8_roofline and ms8.value >= g_ms.value) else dmma_roofline,
     }
+    if int8_roofline:
+        line["roofline_secondary"] = dmma_roofline if ms8.value >= g_ms.value else int8_roofline
     if cholesky is not None:
         cholesky["frac_of_fp64_tensor_peak"] = cholesky["tflops"] / peak
         line["cholesky"] = cholesky

@@ -115,6 +115,9 @@ int pb_options_default(pb_options* options);
 long long pb_launch_count(void);
 int pb_profile_begin(void);
 int pb_profile_end(long long* gemm_launches, double* gemm_ms, double* gemm_flops);
+/* INT8-sliced contractions (oz_gemm_kernel) inside the region closed by the last pb_profile_end: launches, summed
+ * CUDA-event duration, summed FP64-equivalent flops (2 M N K; each launch is 28 exact int8 GEMMs of that shape). */
+int pb_profile_int8(long long* launches, double* ms, double* fp64_equivalent_flops);
 /* FP64 tensor-core (DMMA) peak of the current device in TFLOP/s, from a register-resident mma.sync loop run on the
  * default stream (synchronises it): the denominator of the Cholesky roofline fractions (MEASURED_PEAKS.json has no
  * FP64 entry).  ~50 ms. */

@@ -65,6 +65,7 @@ SIGNATURES = {
     "pb_launch_count": (C.c_longlong, []),
     "pb_profile_begin": (_i32, []),
     "pb_profile_end": (_i32, [C.POINTER(C.c_longlong), C.POINTER(_f64), C.POINTER(_f64)]),
+    "pb_profile_int8": (_i32, [C.POINTER(C.c_longlong), C.POINTER(_f64), C.POINTER(_f64)]),
     "pb_measure_fp64_tensor_peak": (_i32, [C.POINTER(_f64)]),
     "pb_likelihood": (_i32, [_p, _LIK, _p, _p, _i64, _i64, _p, _p, _p, _p]),
     "pb_predictive_distributions": (_i32, [_p, _LIK, _p, _p, _i64, _p]),

@@ -19,7 +19,9 @@ void set_error(const char* fmt, ...) {
 static std::atomic<long long> g_launches{0};
 static std::atomic<int> g_profiling{0};
 static std::mutex g_prof_mu;
-struct GemmRec { cudaEvent_t e0, e1; double flops; long long launches; };
+struct GemmRec { cudaEvent_t e0, e1; double flops; long long launches; int kind; };
+static long long g_int8_launches = 0;      // totals of the INT8 (ozaki.cu) launches of the last profiled region
+static double g_int8_ms = 0, g_int8_flops = 0;
 static std::vector<GemmRec> g_gemm;
 static thread_local CaptureTally* tl_tally = nullptr;
 
@@ -27,9 +29,9 @@ void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void note_launches(long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 bool profiling_enabled() { return g_profiling.load(std::memory_order_relaxed) != 0; }
-void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches) {
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches, int kind) {
     std::lock_guard<std::mutex> lock(g_prof_mu);
-    g_gemm.push_back({e0, e1, flops, launches});
+    g_gemm.push_back({e0, e1, flops, launches, kind});
 }
 void set_capture_tally(CaptureTally* t) { tl_tally = t; }
 CaptureTally* capture_tally() { return tl_tally; }
@@ -45,7 +47,7 @@ static pb_options default_options() {
     o.potrf_lookahead = 1;
     o.potrf_graph = 0;                 // measured slower than eager issue on B200: opt-in
     o.dist_block = 0;
-    o.potrf_ozaki = 0;
+    o.potrf_ozaki = -1;                // auto: INT8 tensor-core contractions for n >= 8192 (1.5 - 1.6 x the DMMA factorisation, profiles/r02_ozaki_bench_*.json)
     o._reserved = 0;
     return o;
 }
@@ -79,19 +81,32 @@ extern "C" int pb_profile_begin(void) {
 extern "C" int pb_profile_end(long long* gemm_launches, double* gemm_ms, double* gemm_flops) {
     pb::g_profiling.store(0);
     std::lock_guard<std::mutex> lock(pb::g_prof_mu);
-    double ms = 0, fl = 0;
+    double ms = 0, fl = 0, ms8 = 0, fl8 = 0;
+    long long launches = 0, launches8 = 0;
     for (auto& r : pb::g_gemm) {
         float t = 0;
-        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) { ms += t; fl += r.flops; }
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+            if (r.kind == 1) { ms8 += t; fl8 += r.flops; launches8 += r.launches; }
+            else { ms += t; fl += r.flops; launches += r.launches; }
+        }
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
     }
-    long long launches = 0;
-    for (auto& r : pb::g_gemm) launches += r.launches;
+    pb::g_int8_launches = launches8; pb::g_int8_ms = ms8; pb::g_int8_flops = fl8;
     if (gemm_launches) *gemm_launches = launches;
     if (gemm_ms) *gemm_ms = ms;
     if (gemm_flops) *gemm_flops = fl;
     pb::g_gemm.clear();
+    return PB_OK;
+}
+
+// The INT8-sliced contractions (oz_gemm_kernel) of the region closed by the last pb_profile_end: launches, summed
+// CUDA-event duration (ms) and summed FP64-EQUIVALENT flops (2 M N K; each is 28 int8 GEMMs of that shape).
+extern "C" int pb_profile_int8(long long* launches, double* ms, double* fp64_equivalent_flops) {
+    std::lock_guard<std::mutex> lock(pb::g_prof_mu);
+    if (launches) *launches = pb::g_int8_launches;
+    if (ms) *ms = pb::g_int8_ms;
+    if (fp64_equivalent_flops) *fp64_equivalent_flops = pb::g_int8_flops;
     return PB_OK;
 }
 

@@ -20,7 +20,7 @@ void note_launch();
 void note_launches(long long n);
 long long launch_count();
 bool profiling_enabled();
-void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches = 1);
+void profile_gemm(cudaEvent_t e0, cudaEvent_t e1, double flops, long long launches = 1, int kind = 0);   // kind 1 = INT8-sliced
 // While a factorisation is being captured into a CUDA graph the GEMM launcher cannot time its launches with events;
 // it adds their algorithmic flops to the capturing thread's tally instead (potrf.cu attributes them to the replay).
 struct CaptureTally { double flops = 0; long long launches = 0; };
@@ -118,9 +118,12 @@ __device__ __forceinline__ double block_sum(double v) {
 // kernels are issue bound on FP64 transcendentals: ncu sm__throughput 74-76 %).
 // Cody-Waite reduction with fdlibm's ln2 split, degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
 // 4e-18), exponent added directly to the high word; returns 0 for x > 707 (e^-707 = 8e-308).  <= 2 ulp.
-// The coefficients live in the constant bank: as FP64 immediates ptxas re-materialises every one of them with two UMOVs
-// in front of each DFMA (the Gram kernel spent 40 % of its issue slots on that); a constant-bank operand costs nothing.
-__constant__ double EXP_NEG_C[14] = {
+// Two coefficient sources.  As FP64 immediates (default) ptxas re-materialises each coefficient with two UMOVs in front
+// of its DFMA; from the constant bank (CONST_BANK) the instruction count drops by a quarter but every evaluation waits
+// on LDC latency and holds more registers.  Measured on B200 (ncu, profiles/r02_hbm_kernels_ncu.md): the Gram kernel
+// (16 independent evaluations per thread, occupancy limited by registers) is 18 % FASTER with immediates, the likelihood
+// kernel (2 evaluations inside a long dependent chain) 5 % faster with the constant bank.
+__constant__ double EXP_NEG_C[11] = {
     1.6059043836821613e-10,   // 1/13!
     2.08767569878681e-09,     // 1/12!
     2.505210838544172e-08,    // 1/11!
@@ -131,20 +134,33 @@ __constant__ double EXP_NEG_C[14] = {
     1.388888888888889e-03,    // 1/6!
     8.333333333333333e-03,    // 1/5!
     4.1666666666666664e-02,   // 1/4!
-    1.6666666666666666e-01,   // 1/3!
-    1.4426950408889634,       // log2 e
-    -6.93147180369123816490e-01,   // -ln2_hi
-    -1.90821492927058770002e-10};  // -ln2_lo
+    1.6666666666666666e-01};  // 1/3!
+template <bool CONST_BANK = false>
 __device__ __forceinline__ double exp_neg(double x) {
     const double MAGIC = 6755399441055744.0;                  // 2^52 + 2^51: rounds to nearest integer
-    const double t = fma(-x, EXP_NEG_C[11], MAGIC);
+    const double t = fma(-x, 1.4426950408889634, MAGIC);
     const int n = __double2loint(t);                          // n = round(-x log2 e) <= 0
     const double nf = t - MAGIC;
-    double r = fma(nf, EXP_NEG_C[12], -x);                    // -x - n ln2_hi (exact product)
-    r = fma(nf, EXP_NEG_C[13], r);                            //      - n ln2_lo
-    double p = EXP_NEG_C[0];
+    double r = fma(nf, -6.93147180369123816490e-01, -x);      // -x - n ln2_hi (exact product)
+    r = fma(nf, -1.90821492927058770002e-10, r);              //      - n ln2_lo
+    double p;
+    if (CONST_BANK) {
+        p = EXP_NEG_C[0];
 #pragma unroll
-    for (int j = 1; j <= 10; ++j) p = fma(p, r, EXP_NEG_C[j]);
+        for (int j = 1; j <= 10; ++j) p = fma(p, r, EXP_NEG_C[j]);
+    } else {
+        p = 1.6059043836821613e-10;                           // 1/13!
+        p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
+        p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
+        p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
+        p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
+        p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
+        p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
+        p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
+        p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
+        p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
+        p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
+    }
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
@@ -170,10 +186,15 @@ bool ozaki_supported(int64_t K);
 int64_t ozaki_scratch_bytes(int64_t rows, int64_t K);
 int ozaki_syrk_lower(cudaStream_t st, int64_t n, int64_t K, double alpha, const double* P, int64_t ldp, double* C,
                      int64_t ldc, void* scratch, int64_t scratch_bytes);
+int ozaki_slice(cudaStream_t st, const double* P, int64_t rows, int64_t K, int64_t ldp, void* scratch, int64_t scratch_bytes);
+int ozaki_apply(cudaStream_t st, int64_t K, const void* a_scratch, int64_t a_rows, int64_t a_off, int64_t M,
+                const void* b_scratch, int64_t b_rows, int64_t b_off, int64_t N, double alpha, double* C, int64_t ldc,
+                bool lower_only);
 int ozaki_gemm_nt(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
                   const double* B, int64_t ldb, double* C, int64_t ldc, void* scratch, int64_t scratch_bytes);
 
 // potrf.cu
+bool ozaki_enabled(int64_t n);      // pb_options.potrf_ozaki resolved for a matrix of order n
 int potrf(cudaStream_t stream, double* A, int64_t n, int64_t lda, void* workspace, int64_t workspace_bytes,
           int32_t* info);
 int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,

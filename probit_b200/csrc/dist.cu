@@ -149,6 +149,8 @@ __global__ void info_decode_kernel(const long long* __restrict__ key, int32_t* _
     *info = *key >= 0 ? (int32_t)(0x7fffffff - *key) : 0;
 }
 
+constexpr int64_t OZ_DIST_MIN_ROWS = 2048;     // smaller updates stay on the DMMA kernels
+
 struct Bc {                      // geometry of the block-column-cyclic layout on this rank
     int64_t n, nb, nblk, ld_loc;
     int world, me;
@@ -157,6 +159,11 @@ struct Bc {                      // geometry of the block-column-cyclic layout o
     int owner(int64_t k) const { return (int)(k % world); }
     double* col(int64_t j) const { return Aloc + (j * nb) * ld_loc + (j / world) * nb; }    // (row j0, first column) of block column j
     int64_t count(int64_t k) const { return nb * 64 + (n - k * nb) * nb; }                    // doubles in panel message k
+    // INT8 path: the rows of panel k BELOW its diagonal block are sliced once (ship_panel); block row j > k starts at
+    // sliced row (j - k - 1) nb.  Only full-width panels with enough rows below them are sliced.
+    int64_t oz_bytes = 0;
+    int64_t sliced_rows(int64_t k) const { return n - (k + 1) * nb; }
+    bool sliced(int64_t k) const { return oz_bytes > 0 && width(k) == nb && sliced_rows(k) >= OZ_DIST_MIN_ROWS; }
 };
 
 Bc make_bc(const Ws& ws) {
@@ -164,12 +171,14 @@ Bc make_bc(const Ws& ws) {
     b.n = ws.L.n; b.nb = ws.L.nb; b.nblk = ws.L.nblk; b.ld_loc = ws.L.ld_loc;
     b.world = ws.L.world; b.me = ws.L.rank;
     b.Aloc = ws.B();
+    b.oz_bytes = ws.L.oz_slice_bytes;
     return b;
 }
 
 // hook(k, k0, w, dinv, P) runs on the main stream once panel k (leaf inverses `dinv` of its diagonal block, rows
 // k0.. of the factor's columns [k0, k0 + w) in `P`, leading dimension nb) is on this rank.
-using PanelHook = std::function<int(int64_t, int64_t, int64_t, const double*, const double*)>;
+// `slices` (may be null) are the digit planes of the panel's rows below its diagonal block (Bc::sliced).
+using PanelHook = std::function<int(int64_t, int64_t, int64_t, const double*, const double*, const void*)>;
 
 enum { EV_RECV = 0, EV_PACKED, EV_TRAIL, EV_COLREADY, EV_COPIED, EV_KINDS };
 
@@ -233,6 +242,11 @@ int pack_panel(cudaStream_t s, const Ws& ws, const Bc& b, int64_t k, const doubl
 int update_column(cudaStream_t s, const Ws& ws, const Bc& b, int64_t j, int64_t k) {
     const double* P = ws.panel(k) + b.nb * 64;
     const int64_t off = (j - k) * b.nb;
+    if (b.sliced(k) && b.n - j * b.nb >= OZ_DIST_MIN_ROWS) {
+        const int64_t so = off - b.nb;             // block row j inside the sliced rows
+        return ozaki_apply(s, b.nb, ws.oz_slice(k), b.sliced_rows(k), so, b.n - j * b.nb, ws.oz_slice(k), b.sliced_rows(k), so,
+                           b.width(j), -1.0, b.col(j), b.ld_loc, false);
+    }
     return gemm_nt(s, b.n - j * b.nb, b.width(j), b.width(k), -1.0, P + off * b.nb, b.nb, P + off * b.nb, b.nb, 1.0, b.col(j),
                    b.ld_loc, false);
 }
@@ -292,6 +306,8 @@ int ship_panel(Comm* c, const Ws& ws, const Bc& b, const Events& ev, int64_t k, 
     if (b.owner(k) == b.me) PB_CUDA(cudaStreamWaitEvent(cs, packed, 0));
     if (tr) tr->mark(TR_BC0, k, cs);
     PB_TRY(comm_broadcast(c, cs, ws.panel(k), b.count(k), b.owner(k)));
+    if (b.sliced(k))       // digit planes of the rows below the diagonal block, into the slicing buffer that goes with this panel buffer
+        PB_TRY(ozaki_slice(cs, ws.panel(k) + b.nb * 64 + b.nb * b.nb, b.sliced_rows(k), b.nb, b.nb, ws.oz_slice(k), b.oz_bytes));
     if (tr) tr->mark(TR_BC1, k, cs);
     PB_CUDA(cudaEventRecord(recv, cs));
     return PB_OK;
@@ -378,6 +394,8 @@ int bc_factor(Comm* c, cudaStream_t st, const Ws& ws, const pb_problem* prob, co
             PB_CUDA(cudaEventRecord(ready, st));
             j += b.world;
         }
+        if (b.sliced(k))                     // tall columns on the INT8 tensor cores, one launch each
+            for (; j < b.nblk && b.n - j * b.nb >= OZ_DIST_MIN_ROWS; j += b.world) PB_TRY(update_column(st, ws, b, j, k));
         if (j < b.nblk) {
             const int64_t count = (b.nblk - 1 - j) / b.world + 1;
             if (count >= 2 && b.nb % 128 == 0 && b.width(k) == b.nb) {
@@ -389,7 +407,7 @@ int bc_factor(Comm* c, cudaStream_t st, const Ws& ws, const pb_problem* prob, co
                 for (; j < b.nblk; j += b.world) PB_TRY(update_column(st, ws, b, j, k));
             }
         }
-        if (hook) PB_TRY(hook(k, k * b.nb, b.width(k), ws.panel(k), ws.panel(k) + b.nb * 64));
+        if (hook) PB_TRY(hook(k, k * b.nb, b.width(k), ws.panel(k), ws.panel(k) + b.nb * 64, b.sliced(k) ? ws.oz_slice(k) : nullptr));
         if (b.owner(k) == b.me) {            // the local copy of column k is refreshed from buffer k % 3: keep the buffer until then
             cudaEvent_t copied;
             PB_TRY(ev.get(EV_COPIED, k, &copied));
@@ -431,7 +449,7 @@ int bc_stream(Comm* c, cudaStream_t st, const Ws& ws, const PanelHook& hook) {
         PB_TRY(ev.get(EV_RECV, k, &recv_k));
         PB_TRY(ev.get(EV_TRAIL, k, &trail_k));
         PB_CUDA(cudaStreamWaitEvent(st, recv_k, 0));
-        PB_TRY(hook(k, k * b.nb, b.width(k), ws.panel(k), ws.panel(k) + b.nb * 64));
+        PB_TRY(hook(k, k * b.nb, b.width(k), ws.panel(k), ws.panel(k) + b.nb * 64, b.sliced(k) ? ws.oz_slice(k) : nullptr));
         PB_CUDA(cudaEventRecord(trail_k, st));
     }
     return PB_OK;
@@ -521,7 +539,9 @@ extern "C" int pb_dist_laplace_fit(pb_stream_t stream, pb_comm* comm, const pb_p
 extern "C" int64_t pb_dist_predict_scratch_bytes(int64_t n, int D, int64_t rows) {
     const int64_t ld = round_up(n > 0 ? n : 1, 16);
     rows = rows > 0 ? rows : 1;
-    return round_up(rows * ld * 8, 256) + round_up(rows * 2 * (int64_t)D * 8, 256) + round_up(64 * rows * 8, 256) + 256;
+    // V (rows x ld) | features of the chunk | partial means | digit planes of one rows x nb block column of V (INT8 path)
+    return round_up(rows * ld * 8, 256) + round_up(rows * 2 * (int64_t)D * 8, 256) + round_up(64 * rows * 8, 256) + 256 +
+           round_up(ozaki_scratch_bytes(rows, 1024), 256);
 }
 
 extern "C" int pb_dist_predict(pb_stream_t stream, pb_comm* comm, const pb_problem* prob, const double* precision,
@@ -549,6 +569,8 @@ extern "C" int pb_dist_predict(pb_stream_t stream, pb_comm* comm, const pb_probl
     double* V = reinterpret_cast<double*>(scratch);
     double* Zs = n_test > 0 ? reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(scratch) + round_up(rows_cap * ldv * 8, 256)) : nullptr;
     double* mean_partial = n_test > 0 ? reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(Zs) + round_up(rows_cap * 2 * (int64_t)D * 8, 256)) : nullptr;
+    void* v_slices = n_test > 0 ? reinterpret_cast<uint8_t*>(mean_partial) + round_up(64 * rows_cap * 8, 256) + 256 : nullptr;
+    const int64_t v_slice_bytes = ozaki_scratch_bytes(rows_cap, 1024);
     const double kss = prob->kernel.scale;          // kernel.elwise(x*, x*) of a stationary kernel (approximators.py:172)
 
     PB_TRY(features(st, prob->kernel, prob->X, n, D, D, ws.Z(), n));
@@ -567,18 +589,22 @@ extern "C" int pb_dist_predict(pb_stream_t stream, pb_comm* comm, const pb_probl
     const bool need_factor = !reuse_factor && (passes > 0 || logdet_host != nullptr);
 
     int64_t m_cur = 0;                              // rows of V in flight during the current pass
-    PanelHook apply = [&](int64_t k, int64_t k0, int64_t w, const double* dinv, const double* P) -> int {
+    PanelHook apply = [&](int64_t k, int64_t k0, int64_t w, const double* dinv, const double* P, const void* slices) -> int {
         (void)k;
         if (m_cur <= 0) return PB_OK;
         // V_k <- V_k L_kk^-T ; V[:, k1:] -= V_k L[k1:, k]^T   (B.solve(K, Kfs) at approximators.py:177, one panel at a time)
         PB_TRY(trsm_right_lt(st, P, w, ws.L.nb, dinv, V + k0, m_cur, ldv));
         const int64_t k1 = k0 + w;
-        if (k1 < n) PB_TRY(gemm_nt(st, m_cur, n - k1, w, -1.0, V + k0, ldv, P + w * ws.L.nb, ws.L.nb, 1.0, V + k1, ldv, false));
-        return PB_OK;
+        if (k1 >= n) return PB_OK;
+        if (slices && m_cur >= 256) {       // the panel's rows below its diagonal block are already sliced: slice V_k and multiply
+            PB_TRY(ozaki_slice(st, V + k0, m_cur, w, ldv, v_slices, v_slice_bytes));
+            return ozaki_apply(st, w, v_slices, m_cur, 0, m_cur, slices, n - k1, 0, n - k1, -1.0, V + k1, ldv, false);
+        }
+        return gemm_nt(st, m_cur, n - k1, w, -1.0, V + k0, ldv, P + w * ws.L.nb, ws.L.nb, 1.0, V + k1, ldv, false);
     };
-    PanelHook apply_and_logdet = [&](int64_t k, int64_t k0, int64_t w, const double* dinv, const double* P) -> int {
+    PanelHook apply_and_logdet = [&](int64_t k, int64_t k0, int64_t w, const double* dinv, const double* P, const void* slices) -> int {
         logdet_add_kernel<<<1, 256, 0, st>>>(P, ws.L.nb, (int)w, ws.scalars() + S_LOGDET); pb::note_launch();
-        return apply(k, k0, w, dinv, P);
+        return apply(k, k0, w, dinv, P, slices);
     };
 
     auto stage_chunk = [&](int64_t r0, int64_t m) -> int {       // mean of the chunk; V = s o k(X*, X) if variances are wanted

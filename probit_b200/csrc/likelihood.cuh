@@ -40,7 +40,7 @@ __device__ __forceinline__ double ncdf_half(double z, const double* tbl) {
 // utilities.py:18-19,31-34: ndtr(z) = 0.5 (1 + erf(z / sqrt 2)), with +-inf mapped to 1 / 0
 __device__ __forceinline__ double norm_cdf(double x, const double* tbl) { return 0.5 + ncdf_half(x, tbl); }
 // utilities.py:22-23; exp(-inf) = 0 for infinite z
-__device__ __forceinline__ double norm_z_pdf(double z) { return OVER_SQRT_2PI * exp_neg(0.5 * z * z); }
+__device__ __forceinline__ double norm_z_pdf(double z) { return OVER_SQRT_2PI * exp_neg<true>(0.5 * z * z); }
 __device__ __forceinline__ double series_h(double z) {   // utilities.py:37-44
     const double q = 1.0 / (z * z);
     return -q + 2.5 * q * q - (37.0 / 3.0) * q * q * q;

@@ -33,6 +33,8 @@ constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;        // 86016 B
 constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + 1024 /* align slack */ + 64 /* barriers */;
 constexpr int OZ_THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int OZ_TMEM_COLS = 512;
+constexpr int OZ_TP = OZ_BN + 1;                         // pitch of the epilogue's staging tile (doubles)
+static_assert(OZ_BM * OZ_TP * 8 <= OZ_STAGES * OZ_STAGE, "staging tile must fit in the pipeline stages");
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
@@ -65,19 +67,36 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 }
 // K-major operand tile, rows at a 64-byte pitch, SWIZZLE_64B (cute::UMMA::SmemDescriptor): start address >> 4,
 // leading byte offset 1 (unused for swizzled K-major), stride byte offset = 8 rows x 64 B = 512 B >> 4, version 1,
-// layout type SWIZZLE_64B = 4
-__device__ __forceinline__ uint64_t oz_smem_desc(uint32_t addr) {
-    return (uint64_t)((addr >> 4) & 0x3fff) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
-}
-__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+// layout type SWIZZLE_64B = 4.
+// The two operand descriptors differ only in their low words (start address >> 4 | LBO << 16), and every plane / K-step
+// offset stays inside the 14-bit address field, so the issuing thread works on 32-bit low words with immediate offsets:
+// 3-4 instructions per UTCIMMA.  (The first version rebuilt both 64-bit descriptors in rolled loops: ~170 cycles of
+// dependent scalar code per MMA on one thread, five times the MMA's own 32 cycles — the tensor pipe sat idle.)
+__device__ __forceinline__ uint32_t oz_desc_lo(uint32_t addr) { return ((addr >> 4) & 0x3fffu) | (1u << 16); }
+constexpr uint32_t OZ_DESC_HI = 32u | (1u << 14) | (4u << 29);   // SBO = 512 B >> 4, version 1, SWIZZLE_64B
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n"
         "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(OZ_IDESC), "r"(accumulate)
+        "r"(a_lo), "r"(b_lo), "r"(OZ_DESC_HI), "r"(OZ_IDESC), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ bool oz_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void oz_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -194,22 +213,25 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // the whole warp walks the loop and one ELECTED lane issues: with `if (lane == 0)` around it ptxas wraps every
+        // UTCIMMA in its own elect-and-branch loop (9 instructions and a branch per MMA)
+        if (oz_elect_one()) {
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % OZ_STAGES;
                 mbar_wait(bars + 8 * s, (kc / OZ_STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a0 = base + s * OZ_STAGE, b0 = a0 + OZ_A_STAGE;
-#pragma unroll 1
+                const uint32_t a_lo = oz_desc_lo(base + s * OZ_STAGE), b_lo = oz_desc_lo(base + s * OZ_STAGE + OZ_A_STAGE);
+                const uint32_t first = kc > 0 ? 1u : 0u;        // the very first MMA of a level overwrites its accumulator
+#pragma unroll
                 for (int t = 2; t <= OZ_S + 1; ++t) {           // level t = p + q -> accumulator t - 2
                     const uint32_t d = tmem + (uint32_t)(t - 2) * OZ_BN;
+#pragma unroll
                     for (int p = 1; p < t; ++p) {
                         const int q = t - p;
-                        const uint64_t ad = oz_smem_desc(a0 + (p - 1) * OZ_A_PLANE);
-                        const uint64_t bd = oz_smem_desc(b0 + (q - 1) * OZ_B_PLANE);
 #pragma unroll
                         for (int ks = 0; ks < OZ_KC / 32; ++ks)    // one UTCIMMA = 32 bytes of K: advance the start address
-                            oz_mma(d, ad + 2 * ks, bd + 2 * ks, (kc > 0 || p > 1 || ks > 0) ? 1u : 0u);
+                            oz_mma(d, a_lo + (uint32_t)((p - 1) * (OZ_A_PLANE >> 4) + 2 * ks),
+                                   b_lo + (uint32_t)((q - 1) * (OZ_B_PLANE >> 4) + 2 * ks), (p == 1 && ks == 0) ? first : 1u);
                     }
                 }
                 oz_commit(bars + 8 * (OZ_STAGES + s));          // frees the stage once these MMAs have read it
@@ -217,19 +239,33 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             oz_commit(bars + 8 * 2 * OZ_STAGES);                // accumulators complete
         }
     } else {
+        const int quarter = warp & 3;                           // TMEM lanes this warp may touch: 32 (warp % 4) ..
+        const int trow = quarter * 32 + lane;                   // row of the tile this thread reads out of TMEM
+        const int64_t row = m0 + trow;
+        const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
+        // while the MMAs run: pull this thread's 512 bytes of C towards L2, so that the read-modify-write at the end
+        // costs L2 latency instead of one serialised DRAM round trip per 16 bytes (the first version: 16 us per tile)
+        if (row < M) {
+            const double* crow = C + row * ldc + n0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (n0 + 16 * i < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16 * i));
+        }
         mbar_wait(bars + 8 * 2 * OZ_STAGES, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int quarter = warp & 3;                           // TMEM lanes this warp may touch: 32 (warp % 4) ..
-        const int64_t row = m0 + quarter * 32 + lane;
-        const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
+        // every TMA load has been consumed and every MMA has retired: the pipeline stages are free and become the
+        // staging tile of the epilogue, T[128][OZ_TP] doubles (odd pitch: conflict-free row-wise 8-byte stores)
+        double* T = reinterpret_cast<double*>(oz_raw + (base - smem_u32(oz_raw)));
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             double acc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-#pragma unroll 1
-            for (int lvl = OZ_S - 1; lvl >= 0; --lvl) {         // least significant level first
-                uint32_t v[32];
+            // int32 -> f64 without the conversion unit (I2F.F64 issues at a fraction of the DFMA rate and was most of the
+            // first version's 30 us per tile): the bits 0x43300000'(v ^ 0x80000000) are the double 2^52 + 2^31 + v, and
+            // subtracting that constant is exact.  Two levels per TMEM round trip, least significant first.
+            const double MAGIC = 4503601774854144.0;            // 2^52 + 2^31
+            auto load32 = [&](int lvl, uint32_t (&v)[32]) {
                 const uint32_t addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -241,28 +277,51 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(addr)
                     : "memory");
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            };
+            auto fold32 = [&](int lvl, const uint32_t (&v)[32]) {
                 const double sc = pow2i(-7 * (lvl + 2));
 #pragma unroll
-                for (int j = 0; j < 32; ++j) acc[j] = fma((double)(int)v[j], sc, acc[j]);
-            }
-            if (row < M) {
-                double* crow = C + row * ldc + n0 + half * 32;
-                const int col0 = n0 + half * 32;
-                const int lim = min(N, lower_only ? (int)min((int64_t)N, row + 1) : N) - col0;     // valid columns of this half
+                for (int j = 0; j < 32; ++j)
+                    acc[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - MAGIC, sc, acc[j]);
+            };
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    const double u0 = rs * colscale[half * 32 + j] * acc[j];
-                    const double u1 = rs * colscale[half * 32 + j + 1] * acc[j + 1];
-                    if (j + 1 < lim) {
-                        double2 c = *reinterpret_cast<double2*>(crow + j);
-                        c.x += u0;
-                        c.y += u1;
-                        *reinterpret_cast<double2*>(crow + j) = c;
-                    } else if (j < lim) {
-                        crow[j] += u0;
-                    }
-                }
+            for (int lvl = OZ_S - 1; lvl >= 0; lvl -= 2) {
+                uint32_t va[32], vb[32];
+                load32(lvl, va);
+                if (lvl >= 1) load32(lvl - 1, vb);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                fold32(lvl, va);
+                if (lvl >= 1) fold32(lvl - 1, vb);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) T[trow * OZ_TP + half * 32 + j] = rs * colscale[half * 32 + j] * acc[j];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+        // C += T with full 512-byte row segments: thread = (row within a group of 4, column pair), 8 rows in flight
+        const int et = threadIdx.x - 64, cp = et & 31, r0 = et >> 5;
+        const int col = n0 + 2 * cp;
+#pragma unroll 1
+        for (int rb = 0; rb < OZ_BM; rb += 32) {
+            double2 c[8];
+            int valid[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int64_t grow = m0 + rb + 4 * i + r0;
+                const int lim = grow < M ? (lower_only ? (int)min((int64_t)N, grow + 1) : N) : 0;   // columns < lim are written
+                valid[i] = col + 1 < lim ? 2 : (col < lim ? 1 : 0);
+                double* p = C + grow * ldc + col;
+                c[i] = make_double2(0.0, 0.0);
+                if (valid[i] == 2) c[i] = *reinterpret_cast<const double2*>(p);
+                else if (valid[i] == 1) c[i].x = *p;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int tr = rb + 4 * i + r0;
+                double* p = C + (int64_t)(m0 + tr) * ldc + col;
+                c[i].x += T[tr * OZ_TP + 2 * cp];
+                c[i].y += T[tr * OZ_TP + 2 * cp + 1];
+                if (valid[i] == 2) *reinterpret_cast<double2*>(p) = c[i];
+                else if (valid[i] == 1) *p = c[i].x;
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -334,7 +393,7 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
                                                      lower_only ? 1 : 0); pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, st));
-        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K);
+        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K, 1, 1);
     }
     PB_CUDA(cudaGetLastError());
     return PB_OK;
@@ -354,6 +413,35 @@ inline int64_t oz_align(int64_t b) { return (b + 255) / 256 * 256; }
 bool ozaki_supported(int64_t K) { return K >= OZ_KC && K % OZ_KC == 0 && K <= 65536; }
 
 int64_t ozaki_scratch_bytes(int64_t rows, int64_t K) { return oz_align(OZ_S * rows * K) + oz_align(4 * rows); }
+
+// Slice once, multiply many times: `scratch` receives the digit planes and exponents of P (rows x K); ozaki_apply then
+// forms  C[M x N] += alpha * A[a_off : a_off + M] B[b_off : b_off + N]^T  from row ranges of two sliced operands (which
+// may be the same one).
+// The Cholesky look-ahead uses this to share one slicing of panel k between the update of block column k + 1 (side
+// stream) and the trailing SYRK (main stream).
+int ozaki_slice(cudaStream_t st, const double* P, int64_t rows, int64_t K, int64_t ldp, void* scratch, int64_t scratch_bytes) {
+    if (rows <= 0) return PB_OK;
+    PB_CHECK(ozaki_supported(K), PB_ERR_INVALID, "ozaki: K must be a multiple of %d", OZ_KC);
+    PB_CHECK(scratch && scratch_bytes >= ozaki_scratch_bytes(rows, K), PB_ERR_INVALID, "ozaki: scratch too small");
+    int8_t* planes = reinterpret_cast<int8_t*>(scratch);
+    int32_t* expo = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(scratch) + oz_align(OZ_S * rows * K));
+    return oz_slice(st, P, rows, K, ldp, planes, expo);
+}
+
+int ozaki_apply(cudaStream_t st, int64_t K, const void* a_scratch, int64_t a_rows, int64_t a_off, int64_t M,
+                const void* b_scratch, int64_t b_rows, int64_t b_off, int64_t N, double alpha, double* C, int64_t ldc,
+                bool lower_only) {
+    if (M <= 0 || N <= 0) return PB_OK;
+    PB_CHECK(a_off >= 0 && b_off >= 0 && a_off + M <= a_rows && b_off + N <= b_rows, PB_ERR_INVALID, "ozaki_apply: row range");
+    PB_CHECK(!lower_only || (M == N && a_off == b_off && a_scratch == b_scratch), PB_ERR_INVALID,
+             "ozaki_apply: lower_only is the SYRK form");
+    PB_CHECK((ldc & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, PB_ERR_INVALID, "ozaki: C must be 16-byte aligned, ld even");
+    const int8_t* ap = reinterpret_cast<const int8_t*>(a_scratch);
+    const int32_t* ae = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(a_scratch) + oz_align(OZ_S * a_rows * K));
+    const int8_t* bp = reinterpret_cast<const int8_t*>(b_scratch);
+    const int32_t* be = reinterpret_cast<const int32_t*>(reinterpret_cast<const uint8_t*>(b_scratch) + oz_align(OZ_S * b_rows * K));
+    return oz_launch(st, M, N, K, alpha, ap + a_off * K, ae + a_off, a_rows, bp + b_off * K, be + b_off, b_rows, C, ldc, lower_only);
+}
 
 // C (lower tiles of the n x n matrix) += alpha * P P^T, P n x K (ld ldp)
 int ozaki_syrk_lower(cudaStream_t st, int64_t n, int64_t K, double alpha, const double* P, int64_t ldp, double* C,

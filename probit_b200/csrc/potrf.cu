@@ -172,7 +172,10 @@ struct Ctx {
     int64_t lda;
     double* dinv;     // (n/64) leaf inverses, 64*64 doubles each, indexed by global column / 64
     int32_t* info;
+    void* oz_scratch = nullptr;   // non-null: the K >= 1024 GEMMs of the solve run on the INT8 tensor cores (ozaki.cu)
+    int64_t oz_bytes = 0;
 };
+constexpr int64_t OZ_TRSM_K = 1024;
 
 inline int64_t split(int64_t n) { return ((n / LEAF + 1) / 2) * LEAF; }   // first-half size, multiple of 64
 
@@ -185,7 +188,17 @@ int trsm_rec(const Ctx& c, double* B, int64_t ldb, int64_t m, const double* L, i
     }
     const int64_t n1 = split(n), n2 = n - n1;
     PB_TRY(trsm_rec(c, B, ldb, m, L, n1, col0));
-    PB_TRY(gemm_nt(c.stream, m, n2, n1, -1.0, B, ldb, L + n1 * c.lda, c.lda, 1.0, B + n1, ldb, false));
+    int64_t k = 0;
+    if (c.oz_scratch && n1 >= OZ_TRSM_K && m >= 256 && n2 >= 256 &&
+        ozaki_scratch_bytes(m, OZ_TRSM_K) + ozaki_scratch_bytes(n2, OZ_TRSM_K) <= c.oz_bytes) {
+        // B2 -= B1 L21^T in K-blocks of 1024: each block slices its m x 1024 and n2 x 1024 operands once (every entry of L
+        // takes part in exactly one GEMM of the recursion, so the factor is sliced once per solve)
+        for (; k + OZ_TRSM_K <= n1; k += OZ_TRSM_K)
+            PB_TRY(ozaki_gemm_nt(c.stream, m, n2, OZ_TRSM_K, -1.0, B + k, ldb, L + n1 * c.lda + k, c.lda, B + n1, ldb, c.oz_scratch,
+                                 c.oz_bytes));
+    }
+    if (k < n1)
+        PB_TRY(gemm_nt(c.stream, m, n2, n1 - k, -1.0, B + k, ldb, L + n1 * c.lda + k, c.lda, 1.0, B + n1, ldb, false));
     return trsm_rec(c, B + n1, ldb, m, L + n1 * c.lda + n1, n2, col0 + n1);
 }
 
@@ -219,8 +232,9 @@ int64_t potrf_inverse_bytes(int64_t n) {
     return ((leaves > 0 ? leaves : 1) * LEAF * LEAF + 2 * (blocks > 0 ? blocks : 1) * 256 * 256) * (int64_t)sizeof(double);
 }
 int potrf_block_size(int64_t n);
-int64_t potrf_ozaki_bytes(int64_t n) { return n >= OZ_MIN_N ? ozaki_scratch_bytes(n, 1024) : 0; }
-static bool ozaki_enabled(int64_t n) {
+// two slicing buffers: the look-ahead slices panel k + 1 while the trailing update of step k still reads panel k's planes
+int64_t potrf_ozaki_bytes(int64_t n) { return n >= OZ_MIN_N ? 2 * ozaki_scratch_bytes(n, 1024) : 0; }
+bool ozaki_enabled(int64_t n) {
     const int mode = opts().potrf_ozaki;
     return n >= OZ_MIN_N && (mode == 1 || (mode < 0 && n >= 8192));
 }
@@ -296,22 +310,31 @@ static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_
     }
 
     Ctx cs{side, lda, reinterpret_cast<double*>(workspace), info};
-    // trailing updates on the INT8 tensor cores: the slicing scratch sits behind the inverses in the workspace
+    // Trailing updates on the INT8 tensor cores (ozaki.cu).  Panel k (all its rows below the diagonal block) is sliced
+    // ONCE, right after it is factored, into buffer k % 2 behind the inverses in the workspace; the side stream's update
+    // of block column k + 1 and the main stream's SYRK both multiply those planes.  Buffer k % 2 is rewritten at step
+    // k + 2 on the side stream, which by then has waited for the SYRK of step k (ev_trail) in step k + 1.
     const bool oz = ozaki_enabled(n) && ozaki_supported(NB) && NB <= 1024;
-    void* oz_scratch = reinterpret_cast<uint8_t*>(workspace) + potrf_inverse_bytes(n);
-    const int64_t oz_bytes = potrf_ozaki_bytes(n);
+    const int64_t oz_half = potrf_ozaki_bytes(n) / 2;
+    uint8_t* oz_base = reinterpret_cast<uint8_t*>(workspace) + potrf_inverse_bytes(n);
+    constexpr int64_t OZ_MIN_ROWS = 2048;            // smaller trailing blocks stay on the DMMA kernel
     EventPool pool;
     cudaEvent_t ev_panel, ev_trail = nullptr;
+    int step = 0;
+    auto slice_panel = [&](cudaStream_t st, int64_t k0, int64_t k1, int buf) -> int {   // rows k1.. of columns [k0, k1)
+        return ozaki_slice(st, A + k1 * lda + k0, n - k1, k1 - k0, lda, oz_base + buf * oz_half, oz_half);
+    };
 
     // panel 0 on the main stream
     {
         const int64_t nb = n < NB ? n : NB;
         PB_TRY(potrf_rec(cm, A, nb, 0));
         PB_TRY(trsm_rec(cm, A + nb * lda, lda, n - nb, A, nb, 0));
+        if (oz && n - nb >= OZ_MIN_ROWS) PB_TRY(slice_panel(stream, 0, nb, 0));
         PB_TRY(pool.get(&ev_panel));
         PB_CUDA(cudaEventRecord(ev_panel, stream));
     }
-    for (int64_t k0 = 0; k0 + NB < n; k0 += NB) {
+    for (int64_t k0 = 0; k0 + NB < n; k0 += NB, ++step) {
         const int64_t nb = NB;                       // panel k is full width here (there are rows below it)
         const int64_t k1 = k0 + nb;                  // first row/col of panel k+1
         const int64_t nb1 = n - k1 < NB ? n - k1 : NB;
@@ -319,15 +342,24 @@ static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_
         const int64_t m2 = n - k2;
         double* P1 = A + k1 * lda + k0;              // rows of panel k belonging to block row k+1 (nb1 x nb)
         double* P2 = A + k2 * lda + k0;              // rows of panel k below that (m2 x nb)
+        const bool oz_k = oz && n - k1 >= OZ_MIN_ROWS;                     // panel k was sliced (buffer step % 2)
+        const bool oz_next = oz && nb1 == NB && n - k2 >= OZ_MIN_ROWS;     // panel k+1 will be
+        const void* planes = oz_base + (step % 2) * oz_half;
 
         // ---- side: bring block column k+1 up to date with panel k, then factor it ----
         PB_CUDA(cudaStreamWaitEvent(side, ev_panel, 0));
         if (ev_trail) PB_CUDA(cudaStreamWaitEvent(side, ev_trail, 0));
         double* A11 = A + k1 * lda + k1;
         PB_TRY(gemm_nt(side, nb1, nb1, nb, -1.0, P1, lda, P1, lda, 1.0, A11, lda, true));
-        if (m2 > 0) PB_TRY(gemm_nt(side, m2, nb1, nb, -1.0, P2, lda, P1, lda, 1.0, A + k2 * lda + k1, lda, false));
+        if (m2 > 0) {
+            if (oz_k && m2 >= OZ_MIN_ROWS)
+                PB_TRY(ozaki_apply(side, nb, planes, n - k1, nb1, m2, planes, n - k1, 0, nb1, -1.0, A + k2 * lda + k1, lda, false));
+            else
+                PB_TRY(gemm_nt(side, m2, nb1, nb, -1.0, P2, lda, P1, lda, 1.0, A + k2 * lda + k1, lda, false));
+        }
         PB_TRY(potrf_rec(cs, A11, nb1, k1));
         if (m2 > 0) PB_TRY(trsm_rec(cs, A + k2 * lda + k1, lda, m2, A11, nb1, k1));
+        if (oz_next) PB_TRY(slice_panel(side, k1, k2, (step + 1) % 2));
         cudaEvent_t ev_next;
         PB_TRY(pool.get(&ev_next));
         PB_CUDA(cudaEventRecord(ev_next, side));
@@ -335,8 +367,8 @@ static int potrf_eager(cudaStream_t stream, cudaStream_t side, double* A, int64_
         // ---- main: the rest of the trailing update with panel k ----
         PB_CUDA(cudaStreamWaitEvent(stream, ev_panel, 0));
         if (m2 > 0) {
-            if (oz && m2 >= 2048)
-                PB_TRY(ozaki_syrk_lower(stream, m2, nb, -1.0, P2, lda, A + k2 * lda + k2, lda, oz_scratch, oz_bytes));
+            if (oz_k && m2 >= OZ_MIN_ROWS)
+                PB_TRY(ozaki_apply(stream, nb, planes, n - k1, nb1, m2, planes, n - k1, nb1, m2, -1.0, A + k2 * lda + k2, lda, true));
             else
                 PB_TRY(gemm_nt(stream, m2, m2, nb, -1.0, P2, lda, P2, lda, 1.0, A + k2 * lda + k2, lda, true));
             PB_TRY(pool.get(&ev_trail));
@@ -506,6 +538,10 @@ int rebuild_solve_workspace(cudaStream_t stream, const double* L, int64_t n, int
 int trsm_right_lt(cudaStream_t stream, const double* L, int64_t n, int64_t ldl, const void* potrf_workspace,
                   double* X, int64_t m, int64_t ldx) {
     Ctx c{stream, ldl, const_cast<double*>(reinterpret_cast<const double*>(potrf_workspace)), nullptr};
+    if (ozaki_enabled(n)) {        // the workspace is the one potrf(n) used: the slicing scratch sits behind the inverses
+        c.oz_scratch = const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(potrf_workspace)) + potrf_inverse_bytes(n);
+        c.oz_bytes = potrf_ozaki_bytes(n);
+    }
     return trsm_rec(c, X, ldx, m, L, n, 0);
 }
 

@@ -30,6 +30,7 @@ struct Layout {
     int world = 1, rank = 0;
     int64_t nb = 0, nblk = 0, owned_max = 0, ld_loc = 0, nloc_max = 0;
     int64_t panel_doubles = 0, panels = 0, dinv_store = 0;
+    int64_t oz_slices = 0, oz_slice_bytes = 0;   // three int8 slicing buffers, one per panel buffer (0 bytes: FP64 DMMA only)
 };
 
 inline Layout make_layout(int64_t n, int D) {
@@ -88,6 +89,9 @@ inline Layout make_dist_layout(int64_t n, int D, int world, int rank) {
     L.panel_doubles = L.nb * 64 + n * L.nb;                   // [leaf inverses of the diagonal block | panel rows]
     L.panels = take(3 * L.panel_doubles * 8);
     L.dinv_store = take(L.owned_max * L.nb * 64 * 8);
+    // trailing updates on the INT8 tensor cores: every arriving panel is sliced once into digit planes (ozaki.cu)
+    L.oz_slice_bytes = (ozaki_enabled(n) && ozaki_supported(L.nb) && L.nb <= 1024) ? ozaki_scratch_bytes(n, L.nb) : 0;
+    L.oz_slices = take(3 * L.oz_slice_bytes);
     L.vec_stride = round_up(world * L.nloc_max, 32);
     L.vec = take(L.vec_stride * V_COUNT * 8);
     L.partial = take(VEC_BLOCKS_MAX * 2 * 8);
@@ -113,6 +117,7 @@ struct Ws {
     int32_t* info() const { return reinterpret_cast<int32_t*>(base + L.info); }
     double* panel(int64_t k) const { return reinterpret_cast<double*>(base + L.panels) + (k % 3) * L.panel_doubles; }
     double* dinv_store() const { return reinterpret_cast<double*>(base + L.dinv_store); }
+    void* oz_slice(int64_t k) const { return L.oz_slice_bytes ? base + L.oz_slices + (k % 3) * L.oz_slice_bytes : nullptr; }
 };
 
 inline unsigned vec_blocks(int64_t n) {

@@ -104,6 +104,52 @@ def test_ozaki_int8_gemm_matches_fp64_product(M, N, K):
         assert torch.equal(Cs[untouched], C0[untouched])
 
 
+@pytest.mark.parametrize("n,nb", [(6000, 0), (9000, 1024), (5200, 768)])
+def test_potrf_with_int8_trailing_updates_matches_lapack(n, nb):
+    """potrf_ozaki = 1: every panel is sliced once into int8 digit planes and both the look-ahead column update and the
+    trailing SYRK multiply those planes on tcgen05 (ozaki.cu, potrf.cu); blocks smaller than 2048 rows stay on DMMA.
+    Held to LAPACK like the FP64 path; strict upper triangle untouched; ragged n (not a multiple of the panel width)."""
+    torch = _torch()
+    from probit_b200 import linalg, _lib
+    rng = np.random.default_rng(n)
+    G = rng.standard_normal((n, 64))
+    A = G @ G.T / 64 + np.diag(rng.uniform(1.0, 3.0, n))            # B-like: identity + low-rank-ish PSD part
+    Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
+    upper = torch.triu(Ad, 1).clone()
+    fac = linalg.potrf_(Ad, options=_lib.default_options(potrf_ozaki=1, potrf_block=nb))
+    L = np.tril(Ad.cpu().numpy())
+    Lref = np.linalg.cholesky(A)
+    assert relerr(L, Lref) < 1e-12
+    assert torch.equal(torch.triu(Ad, 1), upper)
+    b = rng.standard_normal(n)
+    x = linalg.cholesky_solve(fac, torch.as_tensor(b, device="cuda")).cpu().numpy()
+    assert relerr(x, np.linalg.solve(A, b)) < 1e-10
+
+
+def test_int8_right_trsm_and_default_policy_n8192():
+    """Default options switch the K >= 1024 contractions of potrf and of the many-RHS right solve to the INT8 path from
+    n = 8192 on (potrf_ozaki = -1).  Factor and X L^-T against LAPACK, and against the FP64-only path (potrf_ozaki = 0)."""
+    torch = _torch()
+    from probit_b200 import linalg, _lib
+    n = 8192
+    rng = np.random.default_rng(8)
+    G = rng.standard_normal((n, 96))
+    A = G @ G.T / 96 + np.diag(rng.uniform(1.0, 2.0, n))
+    Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
+    fac = linalg.potrf_(Ad)                                           # library defaults
+    Lref = np.linalg.cholesky(A)
+    assert relerr(np.tril(Ad.cpu().numpy()), Lref) < 1e-12
+    Xr = rng.standard_normal((600, n)) * 10.0 ** rng.integers(-3, 4, size=(600, 1))
+    Xd = linalg.empty_matrix(600, n); Xd.copy_(torch.as_tensor(Xr, device="cuda"))
+    linalg.trsm_right_lt_(fac, Xd)
+    ref = sla.solve_triangular(Lref, Xr.T, lower=True).T
+    err = np.abs(Xd.cpu().numpy() - ref).max(axis=1) / np.abs(ref).max(axis=1)
+    assert err.max() < 1e-11, err.max()
+    Bd = linalg.empty_matrix(n, n); Bd.copy_(torch.as_tensor(A, device="cuda"))
+    linalg.potrf_(Bd, options=_lib.default_options(potrf_ozaki=0))
+    assert relerr(np.tril(Bd.cpu().numpy()), np.tril(Ad.cpu().numpy())) < 1e-12
+
+
 @pytest.mark.parametrize("n", [700, 3000, 5000])
 def test_potrf_graph_replay_is_bitwise_identical_to_eager(n):
     """pb_options.potrf_graph: the first call with a given set of buffers runs eagerly, the second captures the two-stream

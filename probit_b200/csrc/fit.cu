@@ -539,7 +539,10 @@ struct Nystrom {
     double* symv = nullptr;   // scratch of the half-traffic symv (null when ld is not padded to 64)
     double* gt = nullptr;     // gemv_t partials: splits x ld
     int64_t stride = 1;       // landmark i is training point i * stride
+    void* oz = nullptr;       // slicing scratch of the INT8 G G^T (r rows x oz_kb columns at a time); null: FP64 DMMA
+    int64_t oz_kb = 0, oz_bytes = 0;
 };
+constexpr int64_t NYSTROM_OZ_KB = 16384;
 
 int64_t nystrom_rank(int64_t n) {
     long long r = opt_nystrom_rank();
@@ -564,6 +567,12 @@ int64_t nystrom_carve(Nystrom& ny, double* base, int64_t n, int64_t ld, int64_t 
     ny.stride = n / ny.r;
     if (sharded) ny.Zl = take((int64_t)Dfmax * ny.r);
     else if (ld >= round_up(n, 64)) ny.symv = take(symv_lower_scratch_doubles(n));
+    if (ozaki_enabled(n) && ny.r >= 1024 && (ldg & 1) == 0) {      // G G^T (r x r x n, rebuilt every Newton step) on the INT8 tensor cores
+        ny.oz_kb = std::min<int64_t>(NYSTROM_OZ_KB, ldg / 64 * 64);
+        ny.oz_bytes = ny.oz_kb >= 1024 ? ozaki_scratch_bytes(ny.r, ny.oz_kb) : 0;
+        ny.oz = ny.oz_bytes ? reinterpret_cast<void*>(take(ny.oz_bytes / 8 + 1)) : nullptr;
+        if (!base) ny.oz = nullptr;
+    }
     return used;
 }
 
@@ -621,6 +630,20 @@ gather_landmarks_kernel(const double* __restrict__ Z, int64_t ldz, int Df, int64
 // Multi-GPU: G is split by columns — rank q holds G[:, lo_q:hi_q] = k(landmarks, X[lo_q:hi_q]) S, generated from the
 // features, forms its r x r x (n/G) share of G G^T on the tensor cores, and ONE all-reduce of the r x r block
 // (134 MB at r = 4096) completes A = K_II + delta I + G G^T on every rank; the r x r Cholesky is replicated.
+// A (lower) += G G^T, G r x K: K-blocks of ny.oz_kb on the INT8 tensor cores (the preconditioner needs no more than a few
+// digits, but the sliced product is exact to 2^-49 anyway), the tail and small problems on the DMMA kernel.
+int nystrom_syrk(cudaStream_t st, const Nystrom& ny, int64_t K, const double* G, int64_t ldg) {
+    int64_t k = 0;
+    if (ny.oz && ny.oz_bytes > 0)
+        for (; K - k >= 1024; ) {
+            const int64_t kb = std::min<int64_t>(ny.oz_kb, (K - k) / 64 * 64);
+            PB_TRY(ozaki_syrk_lower(st, ny.r, kb, 1.0, G + k, ldg, ny.A, ny.lda, ny.oz, ny.oz_bytes));
+            k += kb;
+        }
+    if (k < K) PB_TRY(gemm_nt(st, ny.r, ny.r, K - k, 1.0, G + k, ldg, G + k, ldg, 1.0, ny.A, ny.lda, true));
+    return PB_OK;
+}
+
 int nystrom_build(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, const double* s, double delta, bool* ok,
                   const pb_problem* prob) {
     const int64_t ld = ws.L.ld;
@@ -636,14 +659,14 @@ int nystrom_build(cudaStream_t st, const Ws& ws, const Nystrom& ny, int64_t n, c
         else PB_CUDA(cudaMemsetAsync(ny.A, 0, ny.r * ny.lda * sizeof(double), st));
         if (ny.ncols > 0) {
             PB_TRY(gram_cross(st, prob->kernel, ny.Zl, ny.r, ws.Z() + d.lo, ny.ncols, Df, ny.r, n, ny.G, ny.ldg, s + d.lo));
-            PB_TRY(gemm_nt(st, ny.r, ny.r, ny.ncols, 1.0, ny.G, ny.ldg, ny.G, ny.ldg, 1.0, ny.A, ny.lda, true));
+            PB_TRY(nystrom_syrk(st, ny, ny.ncols, ny.G, ny.ldg));
         }
         PB_TRY(comm_allreduce_sum(d.comm, st, ny.A, ny.r * ny.lda));
     } else {
         dim3 grid((unsigned)std::min<int64_t>(ceil_div<int64_t>(n, 256), 64), (unsigned)ny.r);
         nystrom_prep_kernel<<<grid, 256, 0, st>>>(ws.K(), ld, s, n, ny.r, ny.stride, delta, ny.G, ny.A, ny.lda); pb::note_launch();
         PB_CUDA(cudaGetLastError());
-        PB_TRY(gemm_nt(st, ny.r, ny.r, n, 1.0, ny.G, ld, ny.G, ld, 1.0, ny.A, ny.lda, true));
+        PB_TRY(nystrom_syrk(st, ny, n, ny.G, ld));
     }
     PB_TRY(potrf(st, ny.A, ny.r, ny.lda, ny.pws, ny.pws_bytes, info));
     int32_t info_host = 0;

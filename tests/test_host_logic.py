@@ -60,7 +60,7 @@ def test_workspace_queries_do_not_need_a_gpu():
     ws = lib.pb_fit_workspace_bytes(n, 4)
     assert 2 * n * n * 8 < ws < 2 * n * n * 8 + (3 << 29)          # K + factor (64 GiB of the 180 GB) + two int8 slicing buffers (0.9 GiB)
     inverses = ((n // 64) * 64 * 64 + 2 * (n // 256) * 256 * 256) * 8          # leaf inverses + 256-block inverses and transposes
-    slicing = 7 * n * 1024 + 4 * n                                              # int8 digit planes + row exponents of one panel
+    slicing = 2 * (7 * n * 1024 + 4 * n)                                        # int8 digit planes + row exponents of two panels (look-ahead)
     assert lib.pb_potrf_workspace_bytes(n) == inverses + slicing
     assert lib.pb_potrf_workspace_bytes(1024) == ((1024 // 64) * 64 * 64 + 2 * 4 * 256 * 256) * 8     # below 4096: no slicing scratch
     assert lib.pb_predict_scratch_bytes(n, 4, 4096) >= 4096 * n * 8

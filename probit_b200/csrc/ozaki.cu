@@ -30,11 +30,13 @@ constexpr int OZ_STAGES = 2;
 constexpr int OZ_A_PLANE = OZ_BM * OZ_KC, OZ_B_PLANE = OZ_BN * OZ_KC;
 constexpr int OZ_A_STAGE = OZ_S * OZ_A_PLANE, OZ_B_STAGE = OZ_S * OZ_B_PLANE;
 constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;        // 86016 B
-constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + 1024 /* align slack */ + 64 /* barriers */;
+constexpr int OZ_TP = OZ_BN / 2 + 1;                     // pitch of the epilogue's staging half-tile (doubles; odd: conflict-free)
+constexpr int OZ_T_BYTES = (OZ_BM * OZ_TP * 8 + 127) / 128 * 128;
+constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + OZ_T_BYTES + 1024 /* align slack */ + 64 /* barriers */;
+static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
 constexpr int OZ_THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_TP = OZ_BN + 1;                         // pitch of the epilogue's staging tile (doubles)
-static_assert(OZ_BM * OZ_TP * 8 <= OZ_STAGES * OZ_STAGE, "staging tile must fit in the pipeline stages");
+constexpr int OZ_TILES_PER_CTA = 6;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
@@ -42,6 +44,9 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(O
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -160,30 +165,45 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int K, int64_t ld, i
     if (lane == 0) expo[row] = bad ? 0x7fffffff : e;         // NaN / Inf in the row: poison the outputs it touches
 }
 
+// Each CTA walks a run of up to OZ_TILES_PER_CTA consecutive tiles (consecutive tiles share their row tile, i.e. the A
+// planes in L2), then retires: long enough to amortise the prologue, short enough that the SM is handed back every
+// ~100 us — the Cholesky look-ahead runs its panel work on a high-priority stream UNDER this kernel and needs SMs to
+// free up (a fully persistent grid starved it).  The three roles run as independent pipelines across tile boundaries: the producer keeps the TMA ring full
+// into the next tile while the epilogue is still draining the previous one, the MMA lane starts the next tile as soon as
+// the epilogue has read the accumulators out of TMEM (tmem_empty), and the read-modify-write of C — the part that waits
+// on global memory — overlaps the next tile's MMAs.  (One tile per CTA paid ~17 k cycles of prologue, pipeline fill and
+// serial epilogue per tile: 25 % of a K = 1024 tile, 40 % of a K = 512 one.)
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, double* __restrict__ C, int64_t ldc, int M,
-               int N, int K, double alpha, int lower_only) {
-    int tm, tn;
-    if (lower_only) lower_tile_2to1((int)blockIdx.x, tm, tn);
-    else { tm = (int)blockIdx.y; tn = (int)blockIdx.x; }
-    const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
-    if (m0 >= M || n0 >= N) return;                            // whole CTA, before any barrier / TMEM state exists
-
+               int N, int K, double alpha, int lower_only, int tiles, int tn_count, int tiles_per_cta) {
     extern __shared__ uint8_t oz_raw[];
     const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
-    const uint32_t bars = base + OZ_STAGES * OZ_STAGE;         // full[0..1], empty[0..1], tmem_full
+    const uint32_t stage_t = base + OZ_STAGES * OZ_STAGE;      // epilogue staging: T[128][OZ_TP] doubles (half a tile)
+    const uint32_t bars = stage_t + OZ_T_BYTES;                // full[0..1], empty[0..1], tmem_full, tmem_empty
+    const uint32_t bar_tfull = bars + 8 * 2 * OZ_STAGES, bar_tempty = bar_tfull + 8;
     __shared__ uint32_t tmem_slot;
     __shared__ double colscale[OZ_BN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = K / OZ_KC;
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles, t_begin + tiles_per_cta);
+
+    auto decode = [&](int t, int& m0, int& n0) -> bool {       // false: the tile lies outside the matrix (ragged last row tile)
+        int tm, tn;
+        if (lower_only) lower_tile_2to1(t, tm, tn);
+        else { tm = t / tn_count; tn = t - tm * tn_count; }
+        m0 = tm * OZ_BM;
+        n0 = tn * OZ_BN;
+        return m0 < M && n0 < N;
+    };
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
             mbar_init(bars + 8 * s, 1);
             mbar_init(bars + 8 * (OZ_STAGES + s), 1);
         }
-        mbar_init(bars + 8 * 2 * OZ_STAGES, 1);
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 128);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
@@ -192,10 +212,6 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(OZ_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2) {
-        const int j = threadIdx.x - 64;
-        if (j < OZ_BN) colscale[j] = (n0 + j < N) ? pow2i(eb[n0 + j]) : 0.0;
-    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -203,129 +219,167 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % OZ_STAGES;
-                if (kc >= OZ_STAGES) mbar_wait(bars + 8 * (OZ_STAGES + s), ((kc / OZ_STAGES) - 1) & 1);
-                const uint32_t full = bars + 8 * s;
-                mbar_expect_tx(full, OZ_STAGE);
-                tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
-                tma_load_3d(base + s * OZ_STAGE + OZ_A_STAGE, &mapB, kc * OZ_KC, n0, 0, full);
+            int c = 0;                                          // chunk counter across tiles: stage = c % 2
+            for (int t = t_begin; t < t_end; ++t) {
+                int m0, n0;
+                if (!decode(t, m0, n0)) continue;
+                for (int kc = 0; kc < nk; ++kc, ++c) {
+                    const int s = c % OZ_STAGES;
+                    if (c >= OZ_STAGES) mbar_wait(bars + 8 * (OZ_STAGES + s), ((c / OZ_STAGES) - 1) & 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, OZ_STAGE);
+                    tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
+                    tma_load_3d(base + s * OZ_STAGE + OZ_A_STAGE, &mapB, kc * OZ_KC, n0, 0, full);
+                }
             }
         }
     } else if (warp == 1) {
-        // the whole warp walks the loop and one ELECTED lane issues: with `if (lane == 0)` around it ptxas wraps every
-        // UTCIMMA in its own elect-and-branch loop (9 instructions and a branch per MMA)
+        // one ELECTED lane issues: with `if (lane == 0)` around it ptxas wraps every UTCIMMA in its own elect-and-branch
+        // loop (9 instructions and a branch per MMA)
         if (oz_elect_one()) {
-            for (int kc = 0; kc < nk; ++kc) {
-                const int s = kc % OZ_STAGES;
-                mbar_wait(bars + 8 * s, (kc / OZ_STAGES) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_lo = oz_desc_lo(base + s * OZ_STAGE), b_lo = oz_desc_lo(base + s * OZ_STAGE + OZ_A_STAGE);
-                const uint32_t first = kc > 0 ? 1u : 0u;        // the very first MMA of a level overwrites its accumulator
-#pragma unroll
-                for (int t = 2; t <= OZ_S + 1; ++t) {           // level t = p + q -> accumulator t - 2
-                    const uint32_t d = tmem + (uint32_t)(t - 2) * OZ_BN;
-#pragma unroll
-                    for (int p = 1; p < t; ++p) {
-                        const int q = t - p;
-#pragma unroll
-                        for (int ks = 0; ks < OZ_KC / 32; ++ks)    // one UTCIMMA = 32 bytes of K: advance the start address
-                            oz_mma(d, a_lo + (uint32_t)((p - 1) * (OZ_A_PLANE >> 4) + 2 * ks),
-                                   b_lo + (uint32_t)((q - 1) * (OZ_B_PLANE >> 4) + 2 * ks), (p == 1 && ks == 0) ? first : 1u);
-                    }
+            int c = 0, j = 0;                                   // chunk counter, tile counter of this CTA
+            for (int t = t_begin; t < t_end; ++t) {
+                int m0, n0;
+                if (!decode(t, m0, n0)) continue;
+                if (j > 0) {                                    // the epilogue must have read tile j - 1 out of TMEM
+                    mbar_wait(bar_tempty, (j - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                oz_commit(bars + 8 * (OZ_STAGES + s));          // frees the stage once these MMAs have read it
+                for (int kc = 0; kc < nk; ++kc, ++c) {
+                    const int s = c % OZ_STAGES;
+                    mbar_wait(bars + 8 * s, (c / OZ_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_lo = oz_desc_lo(base + s * OZ_STAGE), b_lo = oz_desc_lo(base + s * OZ_STAGE + OZ_A_STAGE);
+                    const uint32_t first = kc > 0 ? 1u : 0u;    // the very first MMA of a level overwrites its accumulator
+#pragma unroll
+                    for (int lt = 2; lt <= OZ_S + 1; ++lt) {    // level lt = p + q -> accumulator lt - 2
+                        const uint32_t d = tmem + (uint32_t)(lt - 2) * OZ_BN;
+#pragma unroll
+                        for (int p = 1; p < lt; ++p) {
+                            const int q = lt - p;
+#pragma unroll
+                            for (int ks = 0; ks < OZ_KC / 32; ++ks)    // one UTCIMMA = 32 bytes of K: advance the start address
+                                oz_mma(d, a_lo + (uint32_t)((p - 1) * (OZ_A_PLANE >> 4) + 2 * ks),
+                                       b_lo + (uint32_t)((q - 1) * (OZ_B_PLANE >> 4) + 2 * ks), (p == 1 && ks == 0) ? first : 1u);
+                        }
+                    }
+                    oz_commit(bars + 8 * (OZ_STAGES + s));      // frees the stage once these MMAs have read it
+                }
+                oz_commit(bar_tfull);                           // accumulators of this tile complete
+                ++j;
             }
-            oz_commit(bars + 8 * 2 * OZ_STAGES);                // accumulators complete
         }
     } else {
         const int quarter = warp & 3;                           // TMEM lanes this warp may touch: 32 (warp % 4) ..
         const int trow = quarter * 32 + lane;                   // row of the tile this thread reads out of TMEM
-        const int64_t row = m0 + trow;
-        const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
-        // while the MMAs run: pull this thread's 512 bytes of C towards L2, so that the read-modify-write at the end
-        // costs L2 latency instead of one serialised DRAM round trip per 16 bytes (the first version: 16 us per tile)
-        if (row < M) {
-            const double* crow = C + row * ldc + n0;
+        const int et = threadIdx.x - 64;                        // 0 .. 127
+        double* T = reinterpret_cast<double*>(oz_raw + (stage_t - smem_u32(oz_raw)));
+        const double MAGIC = 4503601774854144.0;                // 2^52 + 2^31
+        auto prefetch_tile = [&](int m0, int n0) {              // this thread's 512 bytes of C towards L2 while the MMAs run
+            const int64_t row = m0 + trow;
+            if (row < M) {
+                const double* crow = C + row * ldc + n0;
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (n0 + 16 * i < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16 * i));
+                for (int i = 0; i < 4; ++i)
+                    if (n0 + 16 * i < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16 * i));
+            }
+        };
+        int j = 0;
+        {
+            int m0, n0;
+            for (int t = t_begin; t < t_end; ++t)
+                if (decode(t, m0, n0)) { prefetch_tile(m0, n0); break; }
         }
-        mbar_wait(bars + 8 * 2 * OZ_STAGES, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // every TMA load has been consumed and every MMA has retired: the pipeline stages are free and become the
-        // staging tile of the epilogue, T[128][OZ_TP] doubles (odd pitch: conflict-free row-wise 8-byte stores)
-        double* T = reinterpret_cast<double*>(oz_raw + (base - smem_u32(oz_raw)));
+        for (int t = t_begin; t < t_end; ++t) {
+            int m0, n0;
+            if (!decode(t, m0, n0)) continue;
+            const int64_t row = m0 + trow;
+            const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
+            if (et < OZ_BN) colscale[et] = (n0 + et < N) ? pow2i(eb[n0 + et]) : 0.0;
+            mbar_wait(bar_tfull, j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // colscale visible; T free (previous tile's stores done)
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            double acc[32];
+            for (int half = 0; half < 2; ++half) {
+                double acc[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.0;
-            // int32 -> f64 without the conversion unit (I2F.F64 issues at a fraction of the DFMA rate and was most of the
-            // first version's 30 us per tile): the bits 0x43300000'(v ^ 0x80000000) are the double 2^52 + 2^31 + v, and
-            // subtracting that constant is exact.  Two levels per TMEM round trip, least significant first.
-            const double MAGIC = 4503601774854144.0;            // 2^52 + 2^31
-            auto load32 = [&](int lvl, uint32_t (&v)[32]) {
-                const uint32_t addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(addr)
-                    : "memory");
-            };
-            auto fold32 = [&](int lvl, const uint32_t (&v)[32]) {
-                const double sc = pow2i(-7 * (lvl + 2));
+                for (int jj = 0; jj < 32; ++jj) acc[jj] = 0.0;
+                // int32 -> f64 without the conversion unit (I2F.F64 issues at a fraction of the DFMA rate): the bits
+                // 0x43300000'(v ^ 0x80000000) are the double 2^52 + 2^31 + v, and subtracting that constant is exact.
+                // Two levels per TMEM round trip, least significant first.
+                auto load32 = [&](int lvl, uint32_t (&v)[32]) {
+                    const uint32_t addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ_BN + half * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(addr)
+                        : "memory");
+                };
+                auto fold32 = [&](int lvl, const uint32_t (&v)[32]) {
+                    const double sc = pow2i(-7 * (lvl + 2));
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    acc[j] = fma(__hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - MAGIC, sc, acc[j]);
-            };
+                    for (int jj = 0; jj < 32; ++jj)
+                        acc[jj] = fma(__hiloint2double(0x43300000, (int)(v[jj] ^ 0x80000000u)) - MAGIC, sc, acc[jj]);
+                };
 #pragma unroll
-            for (int lvl = OZ_S - 1; lvl >= 0; lvl -= 2) {
-                uint32_t va[32], vb[32];
-                load32(lvl, va);
-                if (lvl >= 1) load32(lvl - 1, vb);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                fold32(lvl, va);
-                if (lvl >= 1) fold32(lvl - 1, vb);
-            }
+                for (int lvl = OZ_S - 1; lvl >= 0; lvl -= 2) {
+                    uint32_t va[32], vb[32];
+                    load32(lvl, va);
+                    if (lvl >= 1) load32(lvl - 1, vb);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    fold32(lvl, va);
+                    if (lvl >= 1) fold32(lvl - 1, vb);
+                }
+                if (half == 1) {                                // every accumulator has been read: the MMA lane may start the next tile
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(bar_tempty);
+                }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) T[trow * OZ_TP + half * 32 + j] = rs * colscale[half * 32 + j] * acc[j];
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-        // C += T with full 512-byte row segments: thread = (row within a group of 4, column pair), 8 rows in flight
-        const int et = threadIdx.x - 64, cp = et & 31, r0 = et >> 5;
-        const int col = n0 + 2 * cp;
+                for (int jj = 0; jj < 32; ++jj) T[trow * OZ_TP + jj] = rs * colscale[half * 32 + jj] * acc[jj];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // C += T with full 256-byte row segments: thread = (row within a group of 8, column pair), 8 rows in flight
+                const int cp = et & 15, r0 = et >> 4;
+                const int col = n0 + half * 32 + 2 * cp;
 #pragma unroll 1
-        for (int rb = 0; rb < OZ_BM; rb += 32) {
-            double2 c[8];
-            int valid[8];
+                for (int rb = 0; rb < OZ_BM; rb += 64) {
+                    double2 cc[8];
+                    int valid[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t grow = m0 + rb + 4 * i + r0;
-                const int lim = grow < M ? (lower_only ? (int)min((int64_t)N, grow + 1) : N) : 0;   // columns < lim are written
-                valid[i] = col + 1 < lim ? 2 : (col < lim ? 1 : 0);
-                double* p = C + grow * ldc + col;
-                c[i] = make_double2(0.0, 0.0);
-                if (valid[i] == 2) c[i] = *reinterpret_cast<const double2*>(p);
-                else if (valid[i] == 1) c[i].x = *p;
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t grow = m0 + rb + 8 * i + r0;
+                        const int lim = grow < M ? (lower_only ? (int)min((int64_t)N, grow + 1) : N) : 0;   // columns < lim are written
+                        valid[i] = col + 1 < lim ? 2 : (col < lim ? 1 : 0);
+                        const double* pc = C + grow * ldc + col;
+                        cc[i] = make_double2(0.0, 0.0);
+                        if (valid[i] == 2) cc[i] = *reinterpret_cast<const double2*>(pc);
+                        else if (valid[i] == 1) cc[i].x = *pc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int tr = rb + 8 * i + r0;
+                        double* pc = C + (int64_t)(m0 + tr) * ldc + col;
+                        cc[i].x += T[tr * OZ_TP + 2 * cp];
+                        cc[i].y += T[tr * OZ_TP + 2 * cp + 1];
+                        if (valid[i] == 2) *reinterpret_cast<double2*>(pc) = cc[i];
+                        else if (valid[i] == 1) *pc = cc[i].x;
+                    }
+                }
+                if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // T is rewritten by the second half
             }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int tr = rb + 4 * i + r0;
-                double* p = C + (int64_t)(m0 + tr) * ldc + col;
-                c[i].x += T[tr * OZ_TP + 2 * cp];
-                c[i].y += T[tr * OZ_TP + 2 * cp + 1];
-                if (valid[i] == 2) *reinterpret_cast<double2*>(p) = c[i];
-                else if (valid[i] == 1) *p = c[i].x;
+            ++j;
+            {                                                   // C of this CTA's next tile towards L2
+                int m1, n1;
+                for (int t2 = t + 1; t2 < t_end; ++t2)
+                    if (decode(t2, m1, n1)) { prefetch_tile(m1, n1); break; }
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -374,14 +428,10 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
     PB_TRY(oz_map(&mapA, Ap, M, K, a_rows * K, OZ_BM));
     PB_TRY(oz_map(&mapB, Bp, N, K, b_rows * K, OZ_BN));
     const int64_t tm = ceil_div<int64_t>(M, OZ_BM), tn = ceil_div<int64_t>(N, OZ_BN);
-    dim3 grid;
-    if (lower_only) {
-        PB_CHECK(tm * (tm + 1) < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
-        grid = dim3((unsigned)(tm * (tm + 1)), 1, 1);          // column tiles past N exit at once
-    } else {
-        PB_CHECK(tm < 65536, PB_ERR_INVALID, "ozaki: too many row tiles");
-        grid = dim3((unsigned)tn, (unsigned)tm, 1);
-    }
+    const int64_t tiles = lower_only ? tm * (tm + 1) : tm * tn;   // lower: row tile r has column tiles 0 .. 2 r + 1 (those past N are skipped)
+    PB_CHECK(tiles < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
+    const int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms()));
+    const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
     const bool prof = profiling_enabled();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof) {
@@ -390,7 +440,7 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
         PB_CUDA(cudaEventRecord(e0, st));
     }
     oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
-                                                     lower_only ? 1 : 0); pb::note_launch();
+                                                     lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc); pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, st));
         profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K, 1, 1);

@@ -42,17 +42,28 @@ features_kernel(const double* __restrict__ X, int64_t n, int D, int64_t ldx, dou
     }
 }
 
+// sqrt(r2) for r2 >= 0 without the library's special-case branch (5 of the Matern tile's instructions per element were
+// BSSY / BRA / BSYNC around rsqrt's slow path): x = MUFU.RSQ64H seed (2^-22), t = r2 x, e = 1 - r2 x^2,
+// sqrt = t (1 + e/2 + 3 e^2 / 8) with remainder 2.5 e^3 ~ 2^-65; ~1.5 ulp.  Exactly 0 below 1e-300 (the seed flushes
+// subnormals), so k(x, x) = scale exactly.
+__device__ __forceinline__ double sqrt_pos(double r2) {
+    double x;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(r2));
+    const double t = r2 * x;
+    const double e = fma(-t, x, 1.0);
+    const double s = fma(t * e, fma(e, 0.375, 0.5), t);
+    return r2 > 1e-300 ? s : 0.0;
+}
+
 template <int BASE>
 __device__ __forceinline__ double base_eval_t(double scale, double r2) {
     if (BASE == PB_BASE_EQ) return scale * exp_neg(0.5 * r2);
-    const double rho = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;
-    return scale * exp_neg(rho);
+    return scale * exp_neg(sqrt_pos(r2));
 }
 
 __device__ __forceinline__ double base_eval(int base, double scale, double r2) {
     if (base == PB_BASE_EQ) return scale * exp_neg(0.5 * r2);
-    const double rho = r2 > 0.0 ? r2 * rsqrt(r2) : 0.0;       // sqrt(r2), ~1.5 ulp, no denormal/NaN fix-up code
-    return scale * exp_neg(rho);
+    return scale * exp_neg(sqrt_pos(r2));
 }
 
 // Loads the features of 64 points starting at row0 into s[d*64 + r] (zero beyond n).  Features are stored
@@ -105,7 +116,10 @@ __device__ __forceinline__ void tri_tile(int64_t b, int& ti, int& tj) {
 // BASE: kernel family at compile time (no per-element branch); FULL: n is a multiple of 64 and ldk is even,
 // so every tile is interior and no bounds check is compiled in.  One tile per CTA: a persistent variant with
 // register-prefetched features was measured 15-20 % SLOWER (two barriers per tile serialise the three
-// resident CTAs; the hardware overlaps independent one-tile CTAs better).
+// resident CTAs; the hardware overlaps independent one-tile CTAs better).  A variant that walks the tile one group of
+// 16 rows at a time (4 accumulators, 40 registers, 15 % fewer instructions) re-reads the column features from shared
+// memory for every group and ran into the L1TEX limit instead (ncu l1tex throughput 70 - 86 %): no faster for Matern12
+// D = 4, 15 % slower for EQ D = 8 (profiles/r02_hbm_kernels_ncu.md).
 template <int BASE, bool FULL>
 __global__ void __launch_bounds__(256)
 gram_sym_kernel(const double* __restrict__ Z, int64_t n, int Df, int64_t ldz, double* __restrict__ K, int64_t ldk,

@@ -95,10 +95,17 @@ predictive_kernel(const double* __restrict__ mean, const double* __restrict__ va
         }
         if (STAGED) {
             __syncthreads();
-            const int64_t rows = n - base < 256 ? n - base : 256;
-            const int count = (int)rows * J;
-            double* gout = out + base * J;
-            for (int e = threadIdx.x; e < count; e += 256) gout[e] = stage[e];
+            const int rows = n - base < 256 ? (int)(n - base) : 256;
+            const int count = rows * J;
+            double* gout = out + base * J;                       // 2048-byte aligned: base is a multiple of 256
+            if ((count & 1) == 0) {                              // 16-byte copies (always for a full block)
+                const int pairs = count >> 1;
+                const double2* src = reinterpret_cast<const double2*>(stage);
+                double2* dst2 = reinterpret_cast<double2*>(gout);
+                for (int e = threadIdx.x; e < pairs; e += 256) dst2[e] = src[e];
+            } else {
+                for (int e = threadIdx.x; e < count; e += 256) gout[e] = stage[e];
+            }
             __syncthreads();
         }
     }

@@ -36,7 +36,7 @@ constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + OZ_T_BYTES + 1024 /* align slack 
 static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
 constexpr int OZ_THREADS = 192;                          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int OZ_TMEM_COLS = 512;
-constexpr int OZ_TILES_PER_CTA = 6;
+constexpr int OZ_TILES_PER_CTA = 2;
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both
 // K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ_BN >> 3) << 17) | ((uint32_t)(OZ_BM >> 4) << 24);
@@ -165,7 +165,7 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int K, int64_t ld, i
     if (lane == 0) expo[row] = bad ? 0x7fffffff : e;         // NaN / Inf in the row: poison the outputs it touches
 }
 
-// Each CTA walks a run of up to OZ_TILES_PER_CTA consecutive tiles (consecutive tiles share their row tile, i.e. the A
+// Each CTA walks a run of up to OZ_TILES_PER_CTA (2) consecutive tiles (consecutive tiles share their row tile, i.e. the A
 // planes in L2), then retires: long enough to amortise the prologue, short enough that the SM is handed back every
 // ~100 us — the Cholesky look-ahead runs its panel work on a high-priority stream UNDER this kernel and needs SMs to
 // free up (a fully persistent grid starved it).  The three roles run as independent pipelines across tile boundaries: the producer keeps the TMA ring full
@@ -430,7 +430,9 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
     const int64_t tm = ceil_div<int64_t>(M, OZ_BM), tn = ceil_div<int64_t>(N, OZ_BN);
     const int64_t tiles = lower_only ? tm * (tm + 1) : tm * tn;   // lower: row tile r has column tiles 0 .. 2 r + 1 (those past N are skipped)
     PB_CHECK(tiles < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
-    const int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms()));
+    // runs of tiles only where a tile is long (K >= 1024): with short tiles the gain is nil and every extra tile delays the
+    // hand-back of the SM to the look-ahead stream (8-GPU trace: the panel chain, not the trailing update, is the limiter)
+    const int64_t tpc = K >= 1024 ? std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms())) : 1;
     const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
     const bool prof = profiling_enabled();
     cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -55,7 +55,10 @@ def test_gaussian_laplace_is_exact_gp_regression():
 #   False     : knife-edge stopping test or chaotic wandering between several fixed points: no single reference answer
 NEGATIVE_CURVATURE_CASES = [
     (17, 257, 1, 3, "eq", 0.08, True), (21, 400, 2, 4, "matern12", 0.12, True), (4, 600, 3, 4, "eq", 0.18, True),
-    (26, 400, 2, 4, "matern12", 0.12, "weights"),   # 31 iterations, 32 with Phi = erfc(-z / sqrt 2) / 2: same fixed point
+    # 31 iterations, 32 with Phi = erfc(-z / sqrt 2) / 2 (same fixed point on the CPU); the CUDA arithmetic — every piece
+    # within 2 ulp of the reference's — takes 40 steps or lands on ANOTHER fixed point of the same map (12 % away),
+    # depending on the build: several fixed points, reached through ~30 wandering steps
+    (26, 400, 2, 4, "matern12", 0.12, False),
     (27, 300, 1, 3, "eq", 0.1, False),        # 51 / 74 / 90 iterations for three 1-ulp-equivalent Phi, two different fixed points
     (9, 500, 1, 5, "eq", 0.1, False),         # last step 9.5e-6 vs tol 1e-5: the iteration count is a coin toss (7 or 8)
     (3, 350, 1, 3, "matern12", 0.1, False)]   # wanders for ~35 steps and lands on DIFFERENT fixed points (rel. diff 0.3)

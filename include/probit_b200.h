@@ -105,7 +105,8 @@ typedef struct pb_options {
     int32_t potrf_ozaki;          /* trailing updates of the Cholesky factorisation on the INT8 tensor cores (tcgen05
                                      kind::i8 through error-free slicing, pb_ozaki_gemm_nt): -1 = auto (on for n >= 8192),
                                      0 = FP64 DMMA only, 1 = wherever the shapes allow */
-    int32_t _reserved;
+    int32_t ozaki_tile;           /* tile shape of the INT8-sliced contraction: 0 = 128x64, all 7 levels in one pass;
+                                     1 = 128x128, levels 2-5 and 6-8 in two passes (TMEM holds 512 columns) */
 } pb_options;
 int pb_options_default(pb_options* options);
 

@@ -25,7 +25,7 @@ class Options(C.Structure):
     """pb_options: the tunables of the drivers, passed explicitly with every call (no global configuration)."""
     _fields_ = [("laplace_pcg_min_n", C.c_int64), ("laplace_nystrom_rank", C.c_int64), ("laplace_cg_tol", C.c_double),
                 ("negative_curvature_tol", C.c_double), ("potrf_block", C.c_int32), ("potrf_lookahead", C.c_int32),
-                ("potrf_graph", C.c_int32), ("dist_block", C.c_int32), ("potrf_ozaki", C.c_int32), ("_reserved", C.c_int32)]
+                ("potrf_graph", C.c_int32), ("dist_block", C.c_int32), ("potrf_ozaki", C.c_int32), ("ozaki_tile", C.c_int32)]
 
 
 class LikelihoodSpec(C.Structure):

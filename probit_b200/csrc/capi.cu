@@ -48,7 +48,7 @@ static pb_options default_options() {
     o.potrf_graph = 0;                 // measured slower than eager issue on B200: opt-in
     o.dist_block = 0;
     o.potrf_ozaki = -1;                // auto: INT8 tensor-core contractions for n >= 8192 (1.5 - 1.6 x the DMMA factorisation, profiles/r02_ozaki_bench_*.json)
-    o._reserved = 0;
+    o.ozaki_tile = 0;
     return o;
 }
 static const pb_options g_defaults = default_options();

@@ -19,6 +19,7 @@
 // factorisation built on it against LAPACK.
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 namespace pb {
 
@@ -30,7 +31,8 @@ constexpr int OZ_STAGES = 2;
 constexpr int OZ_A_PLANE = OZ_BM * OZ_KC, OZ_B_PLANE = OZ_BN * OZ_KC;
 constexpr int OZ_A_STAGE = OZ_S * OZ_A_PLANE, OZ_B_STAGE = OZ_S * OZ_B_PLANE;
 constexpr int OZ_STAGE = OZ_A_STAGE + OZ_B_STAGE;        // 86016 B
-constexpr int OZ_TP = OZ_BN / 2 + 1;                     // pitch of the epilogue's staging half-tile (doubles; odd: conflict-free)
+constexpr int OZ_TP = OZ_BN / 2 + 2;                     // pitch of the epilogue's staging half-tile (doubles): rows 16-byte aligned
+                                                         // for the bulk reduction, 4-way bank conflicts on the row-wise stores
 constexpr int OZ_T_BYTES = (OZ_BM * OZ_TP * 8 + 127) / 128 * 128;
 constexpr int OZ_SMEM = OZ_STAGES * OZ_STAGE + OZ_T_BYTES + 1024 /* align slack */ + 64 /* barriers */;
 static_assert(OZ_SMEM <= 227 * 1024, "shared memory budget");
@@ -165,6 +167,10 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int K, int64_t ld, i
     if (lane == 0) expo[row] = bad ? 0x7fffffff : e;         // NaN / Inf in the row: poison the outputs it touches
 }
 
+// Debug timeline (PB_OZ_TIMING=<block index>): clock64 of one CTA at the stations below, read back by pb_debug_oz_times.
+__device__ unsigned long long oz_dbg[16];
+enum { DBG_ENTRY = 0, DBG_SETUP, DBG_FIRST_FULL, DBG_LAST_MMA, DBG_TFULL, DBG_DRAINED, DBG_C_DONE, DBG_EXIT, DBG_FIRST_TMA };
+
 // Each CTA walks a run of up to OZ_TILES_PER_CTA (2) consecutive tiles (consecutive tiles share their row tile, i.e. the A
 // planes in L2), then retires: long enough to amortise the prologue, short enough that the SM is handed back every
 // ~100 us — the Cholesky look-ahead runs its panel work on a high-priority stream UNDER this kernel and needs SMs to
@@ -176,17 +182,21 @@ oz_slice_kernel(const double* __restrict__ P, int64_t rows, int K, int64_t ld, i
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, double* __restrict__ C, int64_t ldc, int M,
-               int N, int K, double alpha, int lower_only, int tiles, int tn_count, int tiles_per_cta) {
+               int N, int K, double alpha, int lower_only, int tiles, int tn_count, int tiles_per_cta, int red) {
     extern __shared__ uint8_t oz_raw[];
     const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
     const uint32_t stage_t = base + OZ_STAGES * OZ_STAGE;      // epilogue staging: T[128][OZ_TP] doubles (half a tile)
     const uint32_t bars = stage_t + OZ_T_BYTES;                // full[0..1], empty[0..1], tmem_full, tmem_empty
     const uint32_t bar_tfull = bars + 8 * 2 * OZ_STAGES, bar_tempty = bar_tfull + 8;
     __shared__ uint32_t tmem_slot;
-    __shared__ double colscale[OZ_BN];
+    __shared__ double colscale[2][OZ_BN];                     // by tile parity: the bulk-reduction path has no barrier between a
+                                                             // tile's last read of its scales and the next tile's write
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = K / OZ_KC;
     const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles, t_begin + tiles_per_cta);
+    const bool dbg = (red >> 8) == (int)blockIdx.x + 1;
+    red &= 1;
+    if (dbg && threadIdx.x == 0) oz_dbg[DBG_ENTRY] = clock64();
 
     auto decode = [&](int t, int& m0, int& n0) -> bool {       // false: the tile lies outside the matrix (ragged last row tile)
         int tm, tn;
@@ -216,6 +226,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
+    if (dbg && threadIdx.x == 0) oz_dbg[DBG_SETUP] = clock64();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -230,6 +241,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     mbar_expect_tx(full, OZ_STAGE);
                     tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
                     tma_load_3d(base + s * OZ_STAGE + OZ_A_STAGE, &mapB, kc * OZ_KC, n0, 0, full);
+                    if (dbg && c == 0) oz_dbg[DBG_FIRST_TMA] = clock64();
                 }
             }
         }
@@ -248,6 +260,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int kc = 0; kc < nk; ++kc, ++c) {
                     const int s = c % OZ_STAGES;
                     mbar_wait(bars + 8 * s, (c / OZ_STAGES) & 1);
+                    if (dbg && c == 0) oz_dbg[DBG_FIRST_FULL] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_lo = oz_desc_lo(base + s * OZ_STAGE), b_lo = oz_desc_lo(base + s * OZ_STAGE + OZ_A_STAGE);
                     const uint32_t first = kc > 0 ? 1u : 0u;    // the very first MMA of a level overwrites its accumulator
@@ -266,6 +279,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     oz_commit(bars + 8 * (OZ_STAGES + s));      // frees the stage once these MMAs have read it
                 }
                 oz_commit(bar_tfull);                           // accumulators of this tile complete
+                if (dbg && j == 0) oz_dbg[DBG_LAST_MMA] = clock64();
                 ++j;
             }
         }
@@ -295,8 +309,10 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (!decode(t, m0, n0)) continue;
             const int64_t row = m0 + trow;
             const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
-            if (et < OZ_BN) colscale[et] = (n0 + et < N) ? pow2i(eb[n0 + et]) : 0.0;
+            double* cscale = colscale[j & 1];
+            if (et < OZ_BN) cscale[et] = (n0 + et < N) ? pow2i(eb[n0 + et]) : 0.0;
             mbar_wait(bar_tfull, j & 1);
+            if (dbg && j == 0 && et == 0) oz_dbg[DBG_TFULL] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             asm volatile("bar.sync 1, 128;" ::: "memory");      // colscale visible; T free (previous tile's stores done)
 #pragma unroll 1
@@ -338,13 +354,42 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (half == 1) {                                // every accumulator has been read: the MMA lane may start the next tile
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     mbar_arrive(bar_tempty);
+                    if (dbg && j == 0 && et == 0) oz_dbg[DBG_DRAINED] = clock64();
                 }
+                // the bulk reduction that last read this thread's row of T must have finished with it
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) T[trow * OZ_TP + jj] = rs * colscale[half * 32 + jj] * acc[jj];
+                for (int jj = 0; jj < 32; ++jj) T[trow * OZ_TP + jj] = rs * cscale[half * 32 + jj] * acc[jj];
+                // Interior segment (all 128 rows inside the matrix, all 32 columns inside it and, for the SYRK form, on or
+                // below the diagonal for every row): C += T by ONE asynchronous bulk reduction per row, issued by the thread
+                // that owns the row — the TMA unit performs the 256-byte add in L2, nobody waits for a load, no barrier.
+                // (Timeline of one CTA, K = 512: the load-add-store version spent 5.8 k cycles per half here, RED.F64 4.5 k,
+                // against 1.75 k for draining TMEM and 22 k for the whole mainloop.)
+                const int seg0 = n0 + half * 32;
+                const bool interior = m0 + OZ_BM <= M && seg0 + 32 <= N && (!lower_only || seg0 + 31 <= m0);
+                if (interior && !red) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    double* dst = C + (int64_t)(m0 + trow) * ldc + seg0;
+                    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 256;"
+                                 ::"l"(dst), "r"(stage_t + (uint32_t)(trow * OZ_TP * 8)) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    continue;
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 // C += T with full 256-byte row segments: thread = (row within a group of 8, column pair), 8 rows in flight
                 const int cp = et & 15, r0 = et >> 4;
                 const int col = n0 + half * 32 + 2 * cp;
+                if (red) {
+                    // fire-and-forget: one reduction per element and launch (deterministic), no round trip to wait for
+#pragma unroll 4
+                    for (int tr = r0; tr < OZ_BM; tr += 8) {
+                        const int64_t grow = m0 + tr;
+                        const int lim = grow < M ? (lower_only ? (int)min((int64_t)N, grow + 1) : N) : 0;
+                        double* pc = C + grow * ldc + col;
+                        if (col < lim) atomicAdd(pc, T[tr * OZ_TP + 2 * cp]);
+                        if (col + 1 < lim) atomicAdd(pc + 1, T[tr * OZ_TP + 2 * cp + 1]);
+                    }
+                } else
 #pragma unroll 1
                 for (int rb = 0; rb < OZ_BM; rb += 64) {
                     double2 cc[8];
@@ -371,12 +416,253 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 }
                 if (half == 0) asm volatile("bar.sync 1, 128;" ::: "memory");     // T is rewritten by the second half
             }
+            if (dbg && j == 0 && et == 0) oz_dbg[DBG_C_DONE] = clock64();
             ++j;
             {                                                   // C of this CTA's next tile towards L2
                 int m1, n1;
                 for (int t2 = t + 1; t2 < t_end; ++t2)
                     if (decode(t2, m1, n1)) { prefetch_tile(m1, n1); break; }
             }
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this thread's reductions have left shared memory and landed
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OZ_TMEM_COLS) : "memory");
+        if (dbg && lane == 0) oz_dbg[DBG_EXIT] = clock64();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ 128 x 128, two passes
+// The 128 x 64 kernel above is bound by the shared-memory operand feed of the tensor core (ncu: tensor-core shared
+// wavefronts 64 % with the tensor pipe 46 % active): an M128 N64 K32 int8 MMA reads 6 KB for 32 cycles of math.  With
+// N = 128 the same bytes feed twice the math, but 7 level accumulators x 128 columns exceed TMEM's 512.  So the levels
+// are split over TWO launches that both accumulate into C:
+//     pass LO : levels 2 .. 5  = products (p, q), p + q <= 5   -> planes 1 .. 4 only, 10 products, 4 accumulators (512 cols)
+//     pass HI : levels 6 .. 8  = products with 6 <= p + q <= 8 -> planes 1 .. 7,      18 products, 3 accumulators (384 cols)
+// K is walked 32 bytes at a time (SWIZZLE_32B rows, one UTCIMMA per product and step), 4 / 3 stages of 32 / 56 KB.
+// Same warp roles, tile runs and staged epilogue (32 columns at a time) as above.
+constexpr int OZ2_BM = 128, OZ2_BN = 128, OZ2_KC = 32;
+constexpr int OZ2_PLANE = 128 * OZ2_KC;                   // 4096 B, A and B alike
+constexpr int OZ2_T_BYTES = OZ_T_BYTES;                   // T[128][33] doubles
+constexpr uint32_t OZ2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(OZ2_BN >> 3) << 17) | ((uint32_t)(OZ2_BM >> 4) << 24);
+constexpr uint32_t OZ2_DESC_HI = 16u | (1u << 14) | (6u << 29);     // SBO = 8 rows x 32 B = 256 B >> 4, version 1, SWIZZLE_32B
+template <int NPL> struct Oz2Cfg {
+    static constexpr int STAGES = NPL <= 4 ? 4 : 3;
+    static constexpr int STAGE = 2 * NPL * OZ2_PLANE;
+    static constexpr int SMEM = STAGES * STAGE + OZ2_T_BYTES + 1024 + 128;
+};
+__device__ __forceinline__ void oz2_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        ".reg .b64 da, db;\n"
+        "mov.b64 da, {%1, %3};\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.ne.b32 p, %5, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(OZ2_DESC_HI), "r"(OZ2_IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tri_tile_128(int t, int& tm, int& tn) {      // t -> (tm, tn), tn <= tm
+    int r = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((r + 1) * (r + 2) / 2 <= t) ++r;
+    while (r * (r + 1) / 2 > t) --r;
+    tm = r;
+    tn = t - r * (r + 1) / 2;
+}
+
+template <int NPL, int T0, int NLEV>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+oz2_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, double* __restrict__ C, int64_t ldc, int M,
+                int N, int K, double alpha, int lower_only, int tiles, int tn_count, int tiles_per_cta) {
+    using CF = Oz2Cfg<NPL>;
+    extern __shared__ uint8_t oz_raw[];
+    const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
+    const uint32_t stage_t = base + CF::STAGES * CF::STAGE;
+    const uint32_t bars = stage_t + OZ2_T_BYTES;               // full[S], empty[S], tmem_full, tmem_empty
+    const uint32_t bar_tfull = bars + 8 * 2 * CF::STAGES, bar_tempty = bar_tfull + 8;
+    __shared__ uint32_t tmem_slot;
+    __shared__ double colscale[OZ2_BN];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = K / OZ2_KC;
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles, t_begin + tiles_per_cta);
+
+    auto decode = [&](int t, int& m0, int& n0) {
+        int tm, tn;
+        if (lower_only) tri_tile_128(t, tm, tn);
+        else { tm = t / tn_count; tn = t - tm * tn_count; }
+        m0 = tm * OZ2_BM;
+        n0 = tn * OZ2_BN;
+    };
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < CF::STAGES; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (CF::STAGES + s), 1);
+        }
+        mbar_init(bar_tfull, 1);
+        mbar_init(bar_tempty, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(OZ_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int c = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                int m0, n0;
+                decode(t, m0, n0);
+                for (int kc = 0; kc < nk; ++kc, ++c) {
+                    const int s = c % CF::STAGES;
+                    if (c >= CF::STAGES) mbar_wait(bars + 8 * (CF::STAGES + s), ((c / CF::STAGES) - 1) & 1);
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, CF::STAGE);
+                    tma_load_3d(base + s * CF::STAGE, &mapA, kc * OZ2_KC, m0, 0, full);
+                    tma_load_3d(base + s * CF::STAGE + NPL * OZ2_PLANE, &mapB, kc * OZ2_KC, n0, 0, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (oz_elect_one()) {
+            int c = 0, j = 0;
+            for (int t = t_begin; t < t_end; ++t, ++j) {
+                if (j > 0) {
+                    mbar_wait(bar_tempty, (j - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kc = 0; kc < nk; ++kc, ++c) {
+                    const int s = c % CF::STAGES;
+                    mbar_wait(bars + 8 * s, (c / CF::STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_lo = oz_desc_lo(base + s * CF::STAGE), b_lo = oz_desc_lo(base + s * CF::STAGE + NPL * OZ2_PLANE);
+                    const uint32_t first = kc > 0 ? 1u : 0u;
+#pragma unroll
+                    for (int lt = T0; lt < T0 + NLEV; ++lt) {
+                        const uint32_t d = tmem + (uint32_t)(lt - T0) * OZ2_BN;
+                        bool fresh = true;                      // first product of this level in this step
+#pragma unroll
+                        for (int p = 1; p <= NPL; ++p) {
+                            const int q = lt - p;
+                            if (q < 1 || q > NPL) continue;
+                            oz2_mma(d, a_lo + (uint32_t)((p - 1) * (OZ2_PLANE >> 4)), b_lo + (uint32_t)((q - 1) * (OZ2_PLANE >> 4)),
+                                    fresh ? first : 1u);
+                            fresh = false;
+                        }
+                    }
+                    oz_commit(bars + 8 * (CF::STAGES + s));
+                }
+                oz_commit(bar_tfull);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int trow = quarter * 32 + lane;
+        const int et = threadIdx.x - 64;
+        double* T = reinterpret_cast<double*>(oz_raw + (stage_t - smem_u32(oz_raw)));
+        const double MAGIC = 4503601774854144.0;                // 2^52 + 2^31
+        auto prefetch_tile = [&](int m0, int n0) {
+            const int64_t row = m0 + trow;
+            if (row < M) {
+                const double* crow = C + row * ldc + n0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (n0 + 16 * i < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(crow + 16 * i));
+            }
+        };
+        int j = 0;
+        if (t_begin < t_end) { int m0, n0; decode(t_begin, m0, n0); prefetch_tile(m0, n0); }
+        for (int t = t_begin; t < t_end; ++t, ++j) {
+            int m0, n0;
+            decode(t, m0, n0);
+            const int64_t row = m0 + trow;
+            const double rs = row < M ? alpha * pow2i(ea[row]) : 0.0;
+            colscale[et] = (n0 + et < N) ? pow2i(eb[n0 + et]) : 0.0;
+            mbar_wait(bar_tfull, j & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll 1
+            for (int qd = 0; qd < 4; ++qd) {                    // 32 columns at a time
+                double acc[32];
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) acc[jj] = 0.0;
+                auto load32 = [&](int lvl, uint32_t (&v)[32]) {
+                    const uint32_t addr = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lvl * OZ2_BN + qd * 32);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(addr)
+                        : "memory");
+                };
+                auto fold32 = [&](int lvl, const uint32_t (&v)[32]) {
+                    const double sc = pow2i(-7 * (lvl + T0));
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj)
+                        acc[jj] = fma(__hiloint2double(0x43300000, (int)(v[jj] ^ 0x80000000u)) - MAGIC, sc, acc[jj]);
+                };
+#pragma unroll
+                for (int lvl = NLEV - 1; lvl >= 0; lvl -= 2) {  // least significant level first
+                    uint32_t va[32], vb[32];
+                    load32(lvl, va);
+                    if (lvl >= 1) load32(lvl - 1, vb);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    fold32(lvl, va);
+                    if (lvl >= 1) fold32(lvl - 1, vb);
+                }
+                if (qd == 3) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    mbar_arrive(bar_tempty);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) T[trow * OZ_TP + jj] = rs * colscale[qd * 32 + jj] * acc[jj];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int cp = et & 15, r0 = et >> 4;
+                const int col = n0 + qd * 32 + 2 * cp;
+#pragma unroll 1
+                for (int rb = 0; rb < OZ2_BM; rb += 64) {
+                    double2 cc[8];
+                    int valid[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int64_t grow = m0 + rb + 8 * i + r0;
+                        const int lim = grow < M ? (lower_only ? (int)min((int64_t)N, grow + 1) : N) : 0;
+                        valid[i] = col + 1 < lim ? 2 : (col < lim ? 1 : 0);
+                        const double* pc = C + grow * ldc + col;
+                        cc[i] = make_double2(0.0, 0.0);
+                        if (valid[i] == 2) cc[i] = *reinterpret_cast<const double2*>(pc);
+                        else if (valid[i] == 1) cc[i].x = *pc;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int tr = rb + 8 * i + r0;
+                        double* pc = C + (int64_t)(m0 + tr) * ldc + col;
+                        cc[i].x += T[tr * OZ_TP + 2 * cp];
+                        cc[i].y += T[tr * OZ_TP + 2 * cp + 1];
+                        if (valid[i] == 2) *reinterpret_cast<double2*>(pc) = cc[i];
+                        else if (valid[i] == 1) *pc = cc[i].x;
+                    }
+                }
+                if (qd < 3) asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+            if (t + 1 < t_end) { int m1, n1; decode(t + 1, m1, n1); prefetch_tile(m1, n1); }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -419,8 +705,83 @@ int oz_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t K, int6
     return PB_OK;
 }
 
+// 3-D uint8 map over planes[S][rows][K] for the 128 x 128 kernel: box = 32 K-bytes x 128 rows x npl planes, SWIZZLE_32B
+int oz2_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t K, int64_t plane_stride, int npl) {
+    EncodeTiledFn enc = oz_encode();
+    PB_CHECK(enc != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)OZ_S};
+    cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)plane_stride};
+    cuuint32_t box[3] = {(cuuint32_t)OZ2_KC, 128u, (cuuint32_t)npl};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PB_CHECK(r == CUDA_SUCCESS, PB_ERR_CUDA, "cuTensorMapEncodeTiled (int8 planes, 32B) failed with %d (rows=%lld K=%lld)", (int)r,
+             (long long)rows, (long long)K);
+    return PB_OK;
+}
+
+template <int NPL, int T0, int NLEV>
+int oz2_pass(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const int8_t* Ap, const int32_t* ea, int64_t a_rows,
+             const int8_t* Bp, const int32_t* eb, int64_t b_rows, double* C, int64_t ldc, bool lower_only, int64_t tiles,
+             int64_t tn, int64_t tpc) {
+    using CF = Oz2Cfg<NPL>;
+    static PerDeviceOnce configured;
+    if (configured.first())
+        PB_CUDA(cudaFuncSetAttribute(oz2_gemm_kernel<NPL, T0, NLEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM));
+    CUtensorMap mapA, mapB;
+    PB_TRY(oz2_map(&mapA, Ap, M, K, a_rows * K, NPL));
+    PB_TRY(oz2_map(&mapB, Bp, N, K, b_rows * K, NPL));
+    const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
+    oz2_gemm_kernel<NPL, T0, NLEV><<<grid, OZ_THREADS, CF::SMEM, st>>>(mapA, mapB, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
+                                                                       lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc);
+    pb::note_launch();
+    PB_CUDA(cudaGetLastError());
+    return PB_OK;
+}
+
+// C += alpha A B^T with 128 x 128 tiles in two passes over the levels (see oz2_gemm_kernel)
+int oz2_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const int8_t* Ap, const int32_t* ea,
+               int64_t a_rows, const int8_t* Bp, const int32_t* eb, int64_t b_rows, double* C, int64_t ldc, bool lower_only) {
+    const int64_t tm = ceil_div<int64_t>(M, OZ2_BM), tn = ceil_div<int64_t>(N, OZ2_BN);
+    const int64_t tiles = lower_only ? tm * (tm + 1) / 2 : tm * tn;
+    PB_CHECK(tiles < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
+    const int64_t tpc = K >= 1024 ? std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms())) : 1;
+    const bool prof = profiling_enabled();
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (prof) {
+        PB_CUDA(cudaEventCreate(&e0));
+        PB_CUDA(cudaEventCreate(&e1));
+        PB_CUDA(cudaEventRecord(e0, st));
+    }
+    PB_TRY((oz2_pass<4, 2, 4>(st, M, N, K, alpha, Ap, ea, a_rows, Bp, eb, b_rows, C, ldc, lower_only, tiles, tn, tpc)));
+    PB_TRY((oz2_pass<7, 6, 3>(st, M, N, K, alpha, Ap, ea, a_rows, Bp, eb, b_rows, C, ldc, lower_only, tiles, tn, tpc)));
+    if (prof) {
+        PB_CUDA(cudaEventRecord(e1, st));
+        profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K, 2, 1);
+    }
+    return PB_OK;
+}
+
+// pb_options.ozaki_tile: 0 = 128 x 64 tiles, one pass over all 7 levels; 1 = 128 x 128 tiles, two passes.  The
+// environment variable PB_OZ_TILE (0 / 1) overrides it for the entry points that take no options (tools, tests).
+static bool oz_use_tile128() {
+    static const int env = [] { const char* e = getenv("PB_OZ_TILE"); return e && *e ? atoi(e) : -1; }();
+    return (env >= 0 ? env : opts().ozaki_tile) == 1;
+}
+
+static int oz_timing_block() {      // PB_OZ_TIMING=<block index>: that CTA records its timeline (0 = off, value is index + 1)
+    static const int env = [] { const char* e = getenv("PB_OZ_TIMING"); return e && *e ? atoi(e) + 1 : 0; }();
+    return env;
+}
+static bool oz_use_red() {
+    static const int env = [] { const char* e = getenv("PB_OZ_RED"); return e && *e ? atoi(e) : 0; }();
+    return env == 1;
+}
+
 int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, const int8_t* Ap, const int32_t* ea,
               int64_t a_rows, const int8_t* Bp, const int32_t* eb, int64_t b_rows, double* C, int64_t ldc, bool lower_only) {
+    if (oz_use_tile128()) return oz2_launch(st, M, N, K, alpha, Ap, ea, a_rows, Bp, eb, b_rows, C, ldc, lower_only);
     static PerDeviceOnce configured;
     if (configured.first())
         PB_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
@@ -430,9 +791,9 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
     const int64_t tm = ceil_div<int64_t>(M, OZ_BM), tn = ceil_div<int64_t>(N, OZ_BN);
     const int64_t tiles = lower_only ? tm * (tm + 1) : tm * tn;   // lower: row tile r has column tiles 0 .. 2 r + 1 (those past N are skipped)
     PB_CHECK(tiles < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
-    // runs of tiles only where a tile is long (K >= 1024): with short tiles the gain is nil and every extra tile delays the
-    // hand-back of the SM to the look-ahead stream (8-GPU trace: the panel chain, not the trailing update, is the limiter)
-    const int64_t tpc = K >= 1024 ? std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms())) : 1;
+    // runs of 2 tiles: the second tile's MMAs hide the first tile's C update and half of the prologue; longer runs delay
+    // the hand-back of the SM to the look-ahead stream (8-GPU trace: the panel chain is the limiter there)
+    const int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms()));
     const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
     const bool prof = profiling_enabled();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -442,7 +803,7 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
         PB_CUDA(cudaEventRecord(e0, st));
     }
     oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
-                                                     lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc); pb::note_launch();
+                                                     lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc, (oz_use_red() ? 1 : 0) | (oz_timing_block() << 8)); pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, st));
         profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K, 1, 1);
@@ -542,4 +903,12 @@ extern "C" int pb_ozaki_gemm_nt(pb_stream_t stream, int64_t M, int64_t N, int64_
         return pb::ozaki_syrk_lower(st, M, K, alpha, A, lda, C, ldc, scratch, scratch_bytes);
     }
     return pb::ozaki_gemm_nt(st, M, N, K, alpha, A, lda, B, ldb, C, ldc, scratch, scratch_bytes);
+}
+
+// Debug: the timeline recorded by the CTA named in PB_OZ_TIMING during the LAST oz_gemm_kernel launch (clock64 values:
+// entry, setup done, first full barrier, last MMA issued, accumulators complete, TMEM drained, C updated, exit, first TMA).
+extern "C" int pb_debug_oz_times(unsigned long long* out16) {
+    PB_CUDA(cudaDeviceSynchronize());
+    PB_CUDA(cudaMemcpyFromSymbol(out16, pb::oz_dbg, sizeof(unsigned long long) * 16));
+    return PB_OK;
 }

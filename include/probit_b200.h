@@ -105,8 +105,10 @@ typedef struct pb_options {
     int32_t potrf_ozaki;          /* trailing updates of the Cholesky factorisation on the INT8 tensor cores (tcgen05
                                      kind::i8 through error-free slicing, pb_ozaki_gemm_nt): -1 = auto (on for n >= 8192),
                                      0 = FP64 DMMA only, 1 = wherever the shapes allow */
-    int32_t ozaki_tile;           /* tile shape of the INT8-sliced contraction: 0 = 128x64, all 7 levels in one pass;
-                                     1 = 128x128, levels 2-5 and 6-8 in two passes (TMEM holds 512 columns) */
+    int32_t ozaki_tile;           /* variant of the INT8-sliced contraction kernel: 0 = 128x64 tiles, all 7 levels in one pass
+                                     (default: the fastest measured); 1 = 128x128 tiles, levels 2-5 and 6-8 in two passes
+                                     (TMEM holds 512 columns); 2 = 128x64 with clusters of two CTAs sharing the A tile by TMA
+                                     multicast.  All three give identical results (tests/test_gpu_kernels.py). */
 } pb_options;
 int pb_options_default(pb_options* options);
 
@@ -157,7 +159,10 @@ int pb_copy_lower_add_diag(pb_stream_t stream, const double* K, int64_t n, int64
 /* ---- K7: Cholesky ----------------------------------------------------------------------------
  * In-place lower Cholesky A = L L^T of the row-major lower triangle (strict upper never read or
  * written).  Replaces B.cholesky at Laplace.py:24, VB.py:10,25 and the LU at solvers.py:24.
- * Blocked right-looking; trailing updates are FP64 tensor-core (DMMA) tiles fed by TMA.
+ * Blocked right-looking with one-panel look-ahead.  Trailing updates: for n >= 8192 (pb_options.potrf_ozaki) exact
+ * int8 digit-plane GEMMs on the tcgen05 tensor cores (FP64 by error-free slicing, csrc/ozaki.cu), otherwise FP64
+ * tensor-core (DMMA) tiles fed by TMA.  The workspace holds the 64x64 leaf inverses and 256x256 block inverses the
+ * solves need and, for n >= 4096, two int8 slicing buffers of one 1024-wide panel (7 n KiB + 4 n bytes each).
  * `info` (device int32): 0, or 1-based column of the first non-positive pivot.                   */
 int64_t pb_potrf_workspace_bytes(int64_t n);
 int pb_potrf(pb_stream_t stream, double* A, int64_t n, int64_t lda, void* workspace,

@@ -94,6 +94,27 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t 
         "r"(a_lo), "r"(b_lo), "r"(OZ_DESC_HI), "r"(OZ_IDESC), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// as tma_load_3d, delivered at the same shared-memory offset (and completing the same-offset barrier) in every CTA of `mask`
+__device__ __forceinline__ void tma_load_3d_multicast(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void oz_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ bool oz_elect_one() {
     uint32_t pred;
     asm volatile(
@@ -179,10 +200,17 @@ enum { DBG_ENTRY = 0, DBG_SETUP, DBG_FIRST_FULL, DBG_LAST_MMA, DBG_TFULL, DBG_DR
 // the epilogue has read the accumulators out of TMEM (tmem_empty), and the read-modify-write of C — the part that waits
 // on global memory — overlaps the next tile's MMAs.  (One tile per CTA paid ~17 k cycles of prologue, pipeline fill and
 // serial epilogue per tile: 25 % of a K = 1024 tile, 40 % of a K = 512 one.)
+// CL: clusters of two CTAs work on tiles (tm, 2i) and (tm, 2i + 1), which share their 128 rows of A.  Each CTA fetches
+// its own B tile and HALF of the A tile (64 rows, plane by plane) and multicasts that half into both CTAs' shared memory,
+// so a chunk costs 57 KB of L2 -> SM traffic per CTA instead of 86 KB.  (CTA timeline + ncu: the mainloop runs at 64 % of
+// the tensor rate with 31 B/clk/SM of TMA traffic — the L2 -> SM feed, not the MMA issue, sets the pace.)  A stage may be
+// refilled only when BOTH CTAs have consumed it: the MMA lane's commit arrives on the empty barrier of both CTAs.
+template <bool CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-               const int32_t* __restrict__ ea, const int32_t* __restrict__ eb, double* __restrict__ C, int64_t ldc, int M,
-               int N, int K, double alpha, int lower_only, int tiles, int tn_count, int tiles_per_cta, int red) {
+               const __grid_constant__ CUtensorMap mapA1, const int32_t* __restrict__ ea, const int32_t* __restrict__ eb,
+               double* __restrict__ C, int64_t ldc, int M, int N, int K, double alpha, int lower_only, int tiles, int tn_count,
+               int tiles_per_cta, int red) {
     extern __shared__ uint8_t oz_raw[];
     const uint32_t base = (smem_u32(oz_raw) + 1023u) & ~1023u;
     const uint32_t stage_t = base + OZ_STAGES * OZ_STAGE;      // epilogue staging: T[128][OZ_TP] doubles (half a tile)
@@ -193,24 +221,29 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                                              // tile's last read of its scales and the next tile's write
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = K / OZ_KC;
-    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(tiles, t_begin + tiles_per_cta);
+    // slots: tiles of this CTA (CL: slot i of cluster c is tile 2 i + rank; `tiles` is even and no tile is skipped)
+    const uint32_t crank = CL ? cluster_ctarank() : 0u;
+    const int slots = CL ? tiles / 2 : tiles;
+    const int owner = CL ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int t_begin = owner * tiles_per_cta, t_end = min(slots, t_begin + tiles_per_cta);
     const bool dbg = (red >> 8) == (int)blockIdx.x + 1;
     red &= 1;
     if (dbg && threadIdx.x == 0) oz_dbg[DBG_ENTRY] = clock64();
 
-    auto decode = [&](int t, int& m0, int& n0) -> bool {       // false: the tile lies outside the matrix (ragged last row tile)
+    auto decode = [&](int slot, int& m0, int& n0) -> bool {    // false: the tile lies outside the matrix (ragged last row tile)
+        const int t = CL ? 2 * slot + (int)crank : slot;
         int tm, tn;
         if (lower_only) lower_tile_2to1(t, tm, tn);
         else { tm = t / tn_count; tn = t - tm * tn_count; }
         m0 = tm * OZ_BM;
         n0 = tn * OZ_BN;
-        return m0 < M && n0 < N;
+        return CL || (m0 < M && n0 < N);                        // CL: both CTAs of a pair always walk in lockstep; TMA zero-fills
     };
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) {
             mbar_init(bars + 8 * s, 1);
-            mbar_init(bars + 8 * (OZ_STAGES + s), 1);
+            mbar_init(bars + 8 * (OZ_STAGES + s), CL ? 2 : 1);
         }
         mbar_init(bar_tfull, 1);
         mbar_init(bar_tempty, 128);
@@ -224,6 +257,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL) cluster_sync();                                    // the peer's barriers exist before anything is multicast to them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_slot;
     if (dbg && threadIdx.x == 0) oz_dbg[DBG_SETUP] = clock64();
@@ -239,7 +273,15 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     if (c >= OZ_STAGES) mbar_wait(bars + 8 * (OZ_STAGES + s), ((c / OZ_STAGES) - 1) & 1);
                     const uint32_t full = bars + 8 * s;
                     mbar_expect_tx(full, OZ_STAGE);
-                    tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
+                    if (CL) {
+                        // my half of the A tile, one plane per instruction (the stage keeps [plane][128 rows][64 B]), to both CTAs
+#pragma unroll
+                        for (int pl = 0; pl < OZ_S; ++pl)
+                            tma_load_3d_multicast(base + s * OZ_STAGE + pl * OZ_A_PLANE + crank * (OZ_A_PLANE / 2), &mapA1, kc * OZ_KC,
+                                                  m0 + 64 * (int)crank, pl, full, (uint16_t)3);
+                    } else {
+                        tma_load_3d(base + s * OZ_STAGE, &mapA, kc * OZ_KC, m0, 0, full);
+                    }
                     tma_load_3d(base + s * OZ_STAGE + OZ_A_STAGE, &mapB, kc * OZ_KC, n0, 0, full);
                     if (dbg && c == 0) oz_dbg[DBG_FIRST_TMA] = clock64();
                 }
@@ -264,19 +306,21 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_lo = oz_desc_lo(base + s * OZ_STAGE), b_lo = oz_desc_lo(base + s * OZ_STAGE + OZ_A_STAGE);
                     const uint32_t first = kc > 0 ? 1u : 0u;    // the very first MMA of a level overwrites its accumulator
+                    // Round-robin over the levels: consecutive MMAs go to DIFFERENT accumulators (level lt has 2 (lt - 1)
+                    // MMAs per stage; issued level by level, up to 14 back-to-back MMAs would chain on one accumulator).
 #pragma unroll
-                    for (int lt = 2; lt <= OZ_S + 1; ++lt) {    // level lt = p + q -> accumulator lt - 2
-                        const uint32_t d = tmem + (uint32_t)(lt - 2) * OZ_BN;
+                    for (int i = 0; i < 2 * OZ_S; ++i) {
 #pragma unroll
-                        for (int p = 1; p < lt; ++p) {
-                            const int q = lt - p;
-#pragma unroll
-                            for (int ks = 0; ks < OZ_KC / 32; ++ks)    // one UTCIMMA = 32 bytes of K: advance the start address
-                                oz_mma(d, a_lo + (uint32_t)((p - 1) * (OZ_A_PLANE >> 4) + 2 * ks),
-                                       b_lo + (uint32_t)((q - 1) * (OZ_B_PLANE >> 4) + 2 * ks), (p == 1 && ks == 0) ? first : 1u);
+                        for (int lt = 2; lt <= OZ_S + 1; ++lt) {    // level lt = p + q -> accumulator lt - 2
+                            if (i >= 2 * (lt - 1)) continue;
+                            const int p = i / 2 + 1, q = lt - p, ks = i & 1;   // one UTCIMMA = 32 bytes of K: advance the start address
+                            oz_mma(tmem + (uint32_t)(lt - 2) * OZ_BN, a_lo + (uint32_t)((p - 1) * (OZ_A_PLANE >> 4) + 2 * ks),
+                                   b_lo + (uint32_t)((q - 1) * (OZ_B_PLANE >> 4) + 2 * ks), i == 0 ? first : 1u);
                         }
                     }
-                    oz_commit(bars + 8 * (OZ_STAGES + s));      // frees the stage once these MMAs have read it
+                    // frees the stage once these MMAs have read it (CL: in both CTAs of the pair, whose loads land in both)
+                    if (CL) oz_commit_multicast(bars + 8 * (OZ_STAGES + s), (uint16_t)3);
+                    else oz_commit(bars + 8 * (OZ_STAGES + s));
                 }
                 oz_commit(bar_tfull);                           // accumulators of this tile complete
                 if (dbg && j == 0) oz_dbg[DBG_LAST_MMA] = clock64();
@@ -428,6 +472,7 @@ oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL) cluster_sync();                                    // no multicast write or remote arrive may target a CTA that has left
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(OZ_TMEM_COLS) : "memory");
@@ -690,12 +735,12 @@ EncodeTiledFn oz_encode() {
 }
 
 // 3-D uint8 map over planes[S][rows][K]: box = 64 K-bytes x box_rows x S planes, SWIZZLE_64B, out-of-range rows read 0
-int oz_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t K, int64_t plane_stride, int box_rows) {
+int oz_map(CUtensorMap* map, const int8_t* planes, int64_t rows, int64_t K, int64_t plane_stride, int box_rows, int box_planes) {
     EncodeTiledFn enc = oz_encode();
     PB_CHECK(enc != nullptr, PB_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)OZ_S};
     cuuint64_t strides[2] = {(cuuint64_t)K, (cuuint64_t)plane_stride};
-    cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, (cuuint32_t)OZ_S};
+    cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(planes), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -774,6 +819,11 @@ static int oz_timing_block() {      // PB_OZ_TIMING=<block index>: that CTA reco
     static const int env = [] { const char* e = getenv("PB_OZ_TIMING"); return e && *e ? atoi(e) + 1 : 0; }();
     return env;
 }
+// PB_OZ_CLUSTER=0/1 overrides pb_options.ozaki_tile == 2 (clusters of two CTAs sharing the A tile by TMA multicast)
+static bool oz_use_cluster() {
+    static const int env = [] { const char* e = getenv("PB_OZ_CLUSTER"); return e && *e ? atoi(e) : -1; }();
+    return (env >= 0 ? env : (opts().ozaki_tile == 2 ? 1 : 0)) == 1;
+}
 static bool oz_use_red() {
     static const int env = [] { const char* e = getenv("PB_OZ_RED"); return e && *e ? atoi(e) : 0; }();
     return env == 1;
@@ -783,18 +833,25 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
               int64_t a_rows, const int8_t* Bp, const int32_t* eb, int64_t b_rows, double* C, int64_t ldc, bool lower_only) {
     if (oz_use_tile128()) return oz2_launch(st, M, N, K, alpha, Ap, ea, a_rows, Bp, eb, b_rows, C, ldc, lower_only);
     static PerDeviceOnce configured;
-    if (configured.first())
-        PB_CUDA(cudaFuncSetAttribute(oz_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
-    CUtensorMap mapA, mapB;
-    PB_TRY(oz_map(&mapA, Ap, M, K, a_rows * K, OZ_BM));
-    PB_TRY(oz_map(&mapB, Bp, N, K, b_rows * K, OZ_BN));
-    const int64_t tm = ceil_div<int64_t>(M, OZ_BM), tn = ceil_div<int64_t>(N, OZ_BN);
+    if (configured.first()) {
+        PB_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+        PB_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM));
+    }
+    const int64_t tm = ceil_div<int64_t>(M, OZ_BM);
+    int64_t tn = ceil_div<int64_t>(N, OZ_BN);
+    // pairs of CTAs (clusters of 2) on column tiles 2 i, 2 i + 1 of a row tile: the lower enumeration has 2 r + 2 tiles in
+    // row tile r (always even); a rectangular product pads the column tiles to an even count (the phantom tile is all masks)
+    const bool cluster = oz_use_cluster() && tm * (lower_only ? tm + 1 : tn) >= 2;
+    if (cluster && !lower_only) tn += tn & 1;
+    CUtensorMap mapA, mapB, mapA1;
+    PB_TRY(oz_map(&mapA, Ap, M, K, a_rows * K, OZ_BM, OZ_S));
+    PB_TRY(oz_map(&mapB, Bp, N, K, b_rows * K, OZ_BN, OZ_S));
+    PB_TRY(oz_map(&mapA1, Ap, M, K, a_rows * K, OZ_BM / 2, 1));          // half an A tile, one plane: the multicast unit
     const int64_t tiles = lower_only ? tm * (tm + 1) : tm * tn;   // lower: row tile r has column tiles 0 .. 2 r + 1 (those past N are skipped)
     PB_CHECK(tiles < (1ll << 31), PB_ERR_INVALID, "ozaki: too many tiles");
     // runs of 2 tiles: the second tile's MMAs hide the first tile's C update and half of the prologue; longer runs delay
     // the hand-back of the SM to the look-ahead stream (8-GPU trace: the panel chain is the limiter there)
     const int64_t tpc = std::max<int64_t>(1, std::min<int64_t>(OZ_TILES_PER_CTA, tiles / num_sms()));
-    const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
     const bool prof = profiling_enabled();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (prof) {
@@ -802,8 +859,28 @@ int oz_launch(cudaStream_t st, int64_t M, int64_t N, int64_t K, double alpha, co
         PB_CUDA(cudaEventCreate(&e1));
         PB_CUDA(cudaEventRecord(e0, st));
     }
-    oz_gemm_kernel<<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
-                                                     lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc, (oz_use_red() ? 1 : 0) | (oz_timing_block() << 8)); pb::note_launch();
+    const int flags = (oz_use_red() ? 1 : 0) | (oz_timing_block() << 8);
+    if (cluster) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * ceil_div<int64_t>(tiles / 2, tpc)), 1, 1);
+        cfg.blockDim = dim3(OZ_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = OZ_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PB_CUDA(cudaLaunchKernelEx(&cfg, oz_gemm_kernel<true>, mapA, mapB, mapA1, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
+                                   lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc, flags));
+    } else {
+        const dim3 grid((unsigned)ceil_div<int64_t>(tiles, tpc), 1, 1);
+        oz_gemm_kernel<false><<<grid, OZ_THREADS, OZ_SMEM, st>>>(mapA, mapB, mapA1, ea, eb, C, ldc, (int)M, (int)N, (int)K, alpha,
+                                                                lower_only ? 1 : 0, (int)tiles, (int)tn, (int)tpc, flags);
+    }
+    pb::note_launch();
     if (prof) {
         PB_CUDA(cudaEventRecord(e1, st));
         profile_gemm(e0, e1, lower_only ? (double)N * (double)(N + 1) * (double)K : 2.0 * M * (double)N * (double)K, 1, 1);

@@ -104,8 +104,8 @@ def test_ozaki_int8_gemm_matches_fp64_product(M, N, K):
         assert torch.equal(Cs[untouched], C0[untouched])
 
 
-@pytest.mark.parametrize("n,nb", [(6000, 0), (9000, 1024), (5200, 768)])
-def test_potrf_with_int8_trailing_updates_matches_lapack(n, nb):
+@pytest.mark.parametrize("n,nb,tile", [(6000, 0, 0), (9000, 1024, 0), (5200, 768, 0), (6000, 0, 1), (9000, 1024, 2), (5200, 768, 2)])
+def test_potrf_with_int8_trailing_updates_matches_lapack(n, nb, tile):
     """potrf_ozaki = 1: every panel is sliced once into int8 digit planes and both the look-ahead column update and the
     trailing SYRK multiply those planes on tcgen05 (ozaki.cu, potrf.cu); blocks smaller than 2048 rows stay on DMMA.
     Held to LAPACK like the FP64 path; strict upper triangle untouched; ragged n (not a multiple of the panel width)."""
@@ -116,7 +116,8 @@ def test_potrf_with_int8_trailing_updates_matches_lapack(n, nb):
     A = G @ G.T / 64 + np.diag(rng.uniform(1.0, 3.0, n))            # B-like: identity + low-rank-ish PSD part
     Ad = linalg.empty_matrix(n, n); Ad.copy_(torch.as_tensor(A, device="cuda"))
     upper = torch.triu(Ad, 1).clone()
-    fac = linalg.potrf_(Ad, options=_lib.default_options(potrf_ozaki=1, potrf_block=nb))
+    # tile: kernel variant (pb_options.ozaki_tile) — 0 = 128x64 one pass, 1 = 128x128 two passes, 2 = 2-CTA clusters with multicast
+    fac = linalg.potrf_(Ad, options=_lib.default_options(potrf_ozaki=1, potrf_block=nb, ozaki_tile=tile))
     L = np.tril(Ad.cpu().numpy())
     Lref = np.linalg.cholesky(A)
     assert relerr(L, Lref) < 1e-12

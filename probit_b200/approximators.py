@@ -344,15 +344,30 @@ def _closed_form_value_and_grad(self):
         flat, rebuild = _flatten_scalars(prior_parameters)
         base = self._spec(prior_parameters)
         grads = []
+        objective = None
         for i, t in enumerate(flat):
             h = 1e-6 * max(1.0, abs(t))
             up, dn = list(flat), list(flat)
             up[i], dn[i] = t + h, t - h
             su, sd = self._spec(rebuild(up)), self._spec(rebuild(dn))
-            if (su.stretch_in != sd.stretch_in or su.period != sd.period or su.base != base.base
-                    or su.periodic != base.periodic):
-                raise NotImplementedError("gradients w.r.t. the period / inner stretch of a periodic kernel are not implemented")
+            if su.base != base.base or su.periodic != base.periodic:
+                raise NotImplementedError("a prior parameter that switches the kernel family has no gradient")
+            if su.stretch_in != sd.stretch_in or su.period != sd.period:
+                # The period and the stretch applied BEFORE the periodic map (EQ().periodic(p).stretch(l)) have no closed
+                # form on the GPU (dK/dtheta is not a function of the feature distance alone).  The derivative is taken by
+                # central differences of the objective itself: two more fits + factorisations on the GPU per such
+                # parameter (the reference's examples do not optimise these; both of theirs use the closed form above).
+                if objective is None:
+                    objective = self.objective()
+                hh = 2e-5 * max(1.0, abs(t))
+                up[i], dn[i] = t + hh, t - hh
+                fu = objective((rebuild(up), likelihood_parameters))
+                fd = objective((rebuild(dn), likelihood_parameters))
+                grads.append((fu - fd) / (2 * hh))
+                continue
             grads.append(d_scale * (su.scale - sd.scale) / (2 * h) + d_stretch * (su.stretch_out - sd.stretch_out) / (2 * h))
+        if objective is not None:
+            self._factor_key = None            # the workspace now holds the factor of the last perturbed fit
         g_prior = rebuild(grads)
         if self._kind == _lib.PB_LIK_GAUSSIAN:
             g_lik = (d_sigma,)

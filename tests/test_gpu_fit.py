@@ -519,6 +519,34 @@ def test_value_and_grad_matches_oracle_gradient():
     assert abs(gl_[0] - Gr["sigma"]) < 1e-7 * abs(Gr["sigma"])
 
 
+def test_value_and_grad_period_and_inner_stretch_by_central_differences():
+    """Prior parameters that move the period or the stretch applied before the periodic map have no closed-form kernel
+    derivative on the GPU; value_and_grad differentiates the objective by central differences for those (and keeps the
+    closed form for the others).  Checked against central differences of the ORACLE objective."""
+    from probit_b200 import approximators as PA, kernels as PK, utilities as PU
+    Xr, yr, _, _ = regression_problem(0, 40)
+    prior_o = lambda t: t[2] * OK.EQ().stretch(t[0]).periodic(t[1]).stretch(t[3])
+    prior_p = lambda t: t[2] * PK.EQ().stretch(t[0]).periodic(t[1]).stretch(t[3])
+    th = (0.35, 0.5, 0.9, 1.1)                      # feature lengthscale, period, scale, input stretch
+    lik = (0.25,)
+    o = OA.LaplaceGP((Xr, yr), prior_o, OU.log_gaussian_likelihood, tolerance=1e-11)
+    obj = o.objective()
+    fd = []
+    for i in range(4):
+        h = 1e-5
+        up, dn = list(th), list(th)
+        up[i] += h; dn[i] -= h
+        fd.append((obj((tuple(up), lik)) - obj((tuple(dn), lik))) / (2 * h))
+    p = PA.LaplaceGP((Xr, yr), prior_p, PU.log_gaussian_likelihood, tolerance=1e-11)
+    value, (g_prior, g_lik) = p.value_and_grad()((th, lik))
+    assert abs(value - obj((th, lik))) < TOL * max(1.0, abs(value))
+    for i in range(4):
+        assert abs(g_prior[i] - fd[i]) < 1e-4 * max(1.0, abs(fd[i])), (i, g_prior[i], fd[i])
+    # a second call is not confused by the perturbed fits left in the workspace
+    value2, (g_prior2, _) = p.value_and_grad()((th, lik))
+    assert abs(value2 - value) < 1e-9 * max(1.0, abs(value)) and abs(g_prior2[2] - g_prior[2]) < 1e-7 * max(1.0, abs(g_prior[2]))
+
+
 def test_predict_mean_only_matches_full_predict():
     X, y, params, family = ordinal_problem(9, 300, 2, 3, "eq")
     o, p = _pair(X, y, family)

@@ -612,8 +612,9 @@ def bench_fit(args, env):
             "ops": "int8 multiply-add = 2 ops; achieved = 28 x 2 M N K per launch / CUDA-event time of the launch",
             "fp64_equivalent_tflops": fl8.value / ms8.value * 1e-9,
             "fp64_equivalent_vs_dmma_peak": fl8.value / ms8.value * 1e-9 / peak,
-            "traffic": 628e6, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch (SYRK 8192 x 1024 lower: "
-                                               "algorithmic 596e6 B = digit planes once + C read-modify-write; profiles/r02_oz_gemm_ncu.md)"),
+            "traffic": 750e6, "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE profiled launch (SYRK 8192 x 1024 lower: "
+                                               "500 + 250 MB; algorithmic 596e6 B = digit planes once + C read-modify-write; "
+                                               "profiles/r02_oz_gemm_ncu.json)"),
             "launches": int(n8.value), "kernel_ms_total": ms8.value,
             "peak_source": "2 x " + bf16_src + " (tcgen05 kind::i8 issues at twice the bf16 rate: ncu peak_sustained 16384 vs 8192 ops/clk/SM)",
             "algorithmic_flops_per_step": fl8.value / args.steps,

@@ -86,6 +86,36 @@ def test_kernel_spec_lowering():
         PK.EQ().periodic(1.0).periodic(2.0).lower()
 
 
+def test_lowered_specs_mean_what_the_oracle_kernels_compute():
+    """The flat pb_kernel_spec of an expression tree, evaluated by its documented formula (include/probit_b200.h:
+    k = scale * base(phi(x), phi(y)), phi(x) = T(x / stretch_in) / stretch_out), equals the oracle's (mlkernels-style,
+    node by node) evaluation of the same tree — for every order of stretch / periodic / scale the reference API allows."""
+    import numpy as np
+    from oracle import kernels as OK
+    from probit_b200 import _lib, kernels as PK
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 2, size=(17, 3))
+
+    def from_spec(s, X):
+        U = X / s.stretch_in
+        if s.periodic:
+            U = np.concatenate([np.sin(2 * np.pi * U / s.period), np.cos(2 * np.pi * U / s.period)], axis=1)
+        U = U / s.stretch_out
+        d2 = ((U[:, None, :] - U[None, :, :]) ** 2).sum(-1)
+        return s.scale * (np.exp(-0.5 * d2) if s.base == _lib.PB_BASE_EQ else np.exp(-np.sqrt(d2)))
+
+    trees = [lambda M: 1.7 * M.EQ().stretch(0.6),
+             lambda M: M.Matern12().stretch(1.3) * 0.4,
+             lambda M: 2.0 * M.EQ().stretch(0.7).periodic(0.5),
+             lambda M: M.EQ().periodic(1.5).stretch(2.0),
+             lambda M: 0.9 * M.EQ().stretch(0.35).periodic(0.5).stretch(1.1),
+             lambda M: 3.0 * (0.5 * M.Matern12().stretch(0.8).stretch(1.5)).periodic(0.75)]
+    for tree in trees:
+        ref = tree(OK)(X)
+        got = from_spec(tree(PK).lower(), X)
+        assert np.abs(got - ref).max() < 1e-14 * max(1.0, np.abs(ref).max())
+
+
 def test_likelihood_recognition_has_no_fallback():
     from probit_b200 import _lib, approximators as PA, utilities as PU
     k = PA._likelihood_kind

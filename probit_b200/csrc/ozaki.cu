@@ -6,7 +6,8 @@
 //
 //   slicing   every row of an operand gets one exponent e (max |x| 2^-e in [1/4, 1/2)); the scaled row is cut into S = 7
 //             signed base-128 digits d_1 .. d_S in [-64, 64] by repeated round-to-nearest (each step exact in FP64):
-//             x = 2^e (sum_p d_p 128^-p + r 128^-S), |r| <= 1/2, i.e. 49 bits below the row's leading bit.
+//             x = 2^e (sum_p d_p 128^-p + r 128^-S), |r| <= 1/2, i.e. 49 bits below the row's leading bit (2^-49 .. 2^-48 of
+//             its largest entry; CPU model of the whole scheme: tests/test_int8_slicing_model.py).
 //   products  A B^T = 2^(ea_i + eb_j) sum_{p,q} 128^-(p+q) (A_p B_q^T); every A_p B_q^T is an exact int8 x int8 -> int32
 //             GEMM.  Pairs are grouped by level t = p + q; levels t <= S + 1 are kept (28 products for S = 7, the
 //             dropped ones are below 128^-(S+2)), and the products of one level share one int32 TMEM accumulator.
@@ -14,7 +15,7 @@
 //             two stages), warp 1 = MMA issuer (56 UTCIMMA per stage into 7 accumulators = 448 TMEM columns),
 //             warps 2..5 = epilogue (tcgen05.ld, int32 -> f64, level scaling by exact powers of two, row / column
 //             exponents, C += in FP64).
-// Accuracy: the slicing error is 2^-49 of each ROW's largest entry and the int32 sums are exact; a K = 1024 update of
+// Accuracy: the slicing error is at most 2^-48 of each ROW's largest entry and the int32 sums are exact; a K = 1024 update of
 // O(1) entries is perturbed by ~1e-14 (DMMA: ~3e-15).  tests/test_gpu_kernels.py pins it against FP64 products and the
 // factorisation built on it against LAPACK.
 #include "common.cuh"

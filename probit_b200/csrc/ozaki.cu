@@ -11,10 +11,12 @@
 //   products  A B^T = 2^(ea_i + eb_j) sum_{p,q} 128^-(p+q) (A_p B_q^T); every A_p B_q^T is an exact int8 x int8 -> int32
 //             GEMM.  Pairs are grouped by level t = p + q; levels t <= S + 1 are kept (28 products for S = 7, the
 //             dropped ones are below 128^-(S+2)), and the products of one level share one int32 TMEM accumulator.
-//   kernel    one CTA per 128 x 64 tile of C: warp 0 = TMA producer (3-D box: 64 K-bytes x rows x 7 planes, SWIZZLE_64B,
-//             two stages), warp 1 = MMA issuer (56 UTCIMMA per stage into 7 accumulators = 448 TMEM columns),
-//             warps 2..5 = epilogue (tcgen05.ld, int32 -> f64, level scaling by exact powers of two, row / column
-//             exponents, C += in FP64).
+//   kernel    128 x 64 tiles of C, runs of two tiles per CTA: warp 0 = TMA producer (3-D box: 64 K-bytes x rows x 7 planes,
+//             SWIZZLE_64B, two 86 KB stages), warp 1 = one elected lane issuing 56 UTCIMMA per stage into 7 accumulators
+//             (448 TMEM columns), warps 2..5 = epilogue (tcgen05.ld, exact int32 -> f64, level scaling by exact powers of
+//             two, row / column exponents, C += by asynchronous 256-byte bulk reductions).  Variants behind
+//             pb_options.ozaki_tile: 128 x 128 tiles in two passes over the levels, and clusters of two CTAs sharing the A
+//             tile by TMA multicast — both correct, neither faster.
 // Accuracy: the slicing error is at most 2^-48 of each ROW's largest entry and the int32 sums are exact; a K = 1024 update of
 // O(1) entries is perturbed by ~1e-14 (DMMA: ~3e-15).  tests/test_gpu_kernels.py pins it against FP64 products and the
 // factorisation built on it against LAPACK.
@@ -196,16 +198,18 @@ enum { DBG_ENTRY = 0, DBG_SETUP, DBG_FIRST_FULL, DBG_LAST_MMA, DBG_TFULL, DBG_DR
 // Each CTA walks a run of up to OZ_TILES_PER_CTA (2) consecutive tiles (consecutive tiles share their row tile, i.e. the A
 // planes in L2), then retires: long enough to amortise the prologue, short enough that the SM is handed back every
 // ~100 us — the Cholesky look-ahead runs its panel work on a high-priority stream UNDER this kernel and needs SMs to
-// free up (a fully persistent grid starved it).  The three roles run as independent pipelines across tile boundaries: the producer keeps the TMA ring full
+// free up (a fully persistent grid starved it).  The three roles run as independent pipelines across tile boundaries: the
+// producer keeps the TMA ring full
 // into the next tile while the epilogue is still draining the previous one, the MMA lane starts the next tile as soon as
 // the epilogue has read the accumulators out of TMEM (tmem_empty), and the read-modify-write of C — the part that waits
 // on global memory — overlaps the next tile's MMAs.  (One tile per CTA paid ~17 k cycles of prologue, pipeline fill and
 // serial epilogue per tile: 25 % of a K = 1024 tile, 40 % of a K = 512 one.)
 // CL: clusters of two CTAs work on tiles (tm, 2i) and (tm, 2i + 1), which share their 128 rows of A.  Each CTA fetches
 // its own B tile and HALF of the A tile (64 rows, plane by plane) and multicasts that half into both CTAs' shared memory,
-// so a chunk costs 57 KB of L2 -> SM traffic per CTA instead of 86 KB.  (CTA timeline + ncu: the mainloop runs at 64 % of
-// the tensor rate with 31 B/clk/SM of TMA traffic — the L2 -> SM feed, not the MMA issue, sets the pace.)  A stage may be
-// refilled only when BOTH CTAs have consumed it: the MMA lane's commit arrives on the empty barrier of both CTAs.
+// so a chunk costs 57 KB of L2 -> SM traffic per CTA instead of 86 KB.  A stage may be refilled only when BOTH CTAs have
+// consumed it: the MMA lane's commit arrives on the empty barrier of both CTAs.  MEASURED (profiles/r02_oz_cta_timeline.txt):
+// the mainloop stays at 2790 cycles per 56-MMA chunk with or without the multicast — the L2 -> SM feed was NOT what set
+// the pace (the M128 N64 K32 int8 MMA itself takes ~50 cycles) — so this variant is opt-in (pb_options.ozaki_tile = 2).
 template <bool CL>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 oz_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
